@@ -1,0 +1,63 @@
+"""In-tree build of the C-ABI shared library (nvcc, sm_100a only). No JIT cache: the .so lives next to this file
+so that it travels with the repo snapshot to the GPU box."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SOURCES = ["gemm_tc.cu", "rowops.cu", "graph.cu", "attention.cu", "builder.cu"]
+LIB_PATH = os.path.join(HERE, "libdgdm_b200.so")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "--use_fast_math=false"]
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    return "nvcc"
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh"),
+                                                       os.path.join(HERE, "..", "include", "dgdm_b200.h")]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source for sm_100a and link libdgdm_b200.so. Returns the library path."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = _nvcc()
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    procs = []
+    for s in SOURCES:
+        src = os.path.join(CSRC, s)
+        if not os.path.exists(src):
+            continue
+        obj = os.path.join(objdir, s.replace(".cu", ".o"))
+        cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        procs.append((s, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    objs = []
+    for s, obj, p in procs:
+        out, _ = p.communicate()
+        if verbose and out:
+            print(out)
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {s}:\n{out}")
+        objs.append(obj)
+    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-lcudart"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}")
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,227 @@
+"""TissueGraphBuilder — drop-in for preprocessing/tissue_graph_builder.py:42-447 (build_graph path).
+
+The O(N^2) parts (768-d Gram / Euclidean kNN / cosine, 2-D kNN) run on the GPU through the C-ABI; candidate
+filtering, duplicate removal and edge emission reproduce the reference's order exactly with vectorised numpy
+(the reference uses Python loops over dataclass objects; the result — indices AND order — is the same).
+"""
+import ctypes as C
+import logging
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .graph import Data
+from .ops import KernelError, _check, _p, _stream
+
+
+@dataclass
+class PatchInfo:
+    """preprocessing/slide_processor.py:34-43."""
+    x: int
+    y: int
+    level: int
+    magnification: float
+    patch_id: str
+    tissue_percentage: float
+    features: Optional[np.ndarray] = None
+
+
+@dataclass
+class SlideData:
+    """preprocessing/slide_processor.py:46-53."""
+    slide_id: str
+    patches: List[PatchInfo]
+    metadata: Dict
+    thumbnail: Optional[np.ndarray] = None
+    tissue_mask: Optional[np.ndarray] = None
+
+
+@dataclass
+class GraphNode:
+    node_id: str
+    patch_info: PatchInfo
+    features: np.ndarray
+    spatial_coords: Tuple[float, float]
+    tissue_type: Optional[str] = None
+    confidence: float = 1.0
+
+
+@dataclass
+class GraphEdge:
+    source_id: str
+    target_id: str
+    edge_type: str
+    weight: float
+    features: Optional[np.ndarray] = None
+
+
+def knn_cosine(features, k, q0=0, nq=None, chunk=None):
+    """features: float32 CUDA [n,d]. Returns (idx int32 [nq,k], cos float32 [nq,k], dist float64 [nq,k]) for rows q0..q0+nq."""
+    lib = _lib.load()
+    n, d = features.shape
+    nq = n - q0 if nq is None else nq
+    dev = features.device
+    idx = torch.empty(nq, k, dtype=torch.int32, device=dev)
+    cos = torch.empty(nq, k, dtype=torch.float32, device=dev)
+    dist = torch.empty(nq, k, dtype=torch.float64, device=dev)
+    if chunk is None:
+        chunk = max(64, min(nq, int(2e9 // (8 * n))))          # <= 2 GB of fp64 distance rows per call
+    for c0 in range(0, nq, chunk):
+        cn = min(chunk, nq - c0)
+        wb = int(lib.dgdm_knn_cosine_work_bytes(cn, n, d, k))
+        work = torch.empty(wb, dtype=torch.uint8, device=dev)
+        _check(lib.dgdm_knn_cosine(_p(features), n, d, q0 + c0, cn, k, _p(idx[c0:]), _p(cos[c0:]), _p(dist[c0:]), _p(work), wb,
+                                   _stream()), "dgdm_knn_cosine")
+    return idx, cos, dist
+
+
+def knn2d(coords, k, q0=0, nq=None, chunk=None):
+    """coords: float64 CUDA [n,2]. Returns (idx int32 [nq,k], dist float64 [nq,k])."""
+    lib = _lib.load()
+    n = coords.size(0)
+    nq = n - q0 if nq is None else nq
+    dev = coords.device
+    idx = torch.empty(nq, k, dtype=torch.int32, device=dev)
+    dist = torch.empty(nq, k, dtype=torch.float64, device=dev)
+    if chunk is None:
+        chunk = max(64, min(nq, int(2e9 // (8 * n))))
+    for c0 in range(0, nq, chunk):
+        cn = min(chunk, nq - c0)
+        _check(lib.dgdm_knn2d(_p(coords), n, q0 + c0, cn, k, _p(idx[c0:]), _p(dist[c0:]), _stream()), "dgdm_knn2d")
+    return idx, dist
+
+
+def candidate_edges(sp_idx, sp_dist, mo_idx, mo_cos, threshold, row0=0):
+    """Reference loops :302-318 and :337-350 vectorised. Inputs are numpy [nq,k+1] arrays for query rows row0..;
+    column 0 (self) is skipped. Returns dict of flat arrays in the reference's emission order (spatial then morphological,
+    row-major): src, tgt, type(0/1), weight float64, f0, f1 (edge features zero-padded to width 2, P7)."""
+    out = []
+    if sp_idx is not None and sp_idx.shape[1] > 1:
+        d = sp_dist[:, 1:]
+        w = np.exp(-d * 10)
+        keep = w >= threshold
+        src = np.broadcast_to(np.arange(sp_idx.shape[0])[:, None] + row0, d.shape)
+        out.append((src[keep], sp_idx[:, 1:][keep].astype(np.int64), np.zeros(int(keep.sum()), np.int64), w[keep], d[keep], w[keep]))
+    if mo_idx is not None and mo_idx.shape[1] > 1:
+        s = mo_cos[:, 1:]
+        keep = s >= np.float32(threshold)
+        src = np.broadcast_to(np.arange(mo_idx.shape[0])[:, None] + row0, s.shape)
+        sv = s[keep].astype(np.float64)
+        out.append((src[keep], mo_idx[:, 1:][keep].astype(np.int64), np.ones(int(keep.sum()), np.int64), sv, sv, np.zeros_like(sv)))
+    if not out:
+        z = np.zeros(0)
+        return dict(src=z.astype(np.int64), tgt=z.astype(np.int64), type=z.astype(np.int64), weight=z, f0=z, f1=z)
+    cat = [np.concatenate([o[i] for o in out]) for i in range(6)]
+    return dict(src=cat[0].astype(np.int64), tgt=cat[1], type=cat[2], weight=cat[3], f0=cat[4], f1=cat[5])
+
+
+def remove_duplicate_edges(e, n):
+    """_remove_duplicate_edges (:354-365): undirected key, strictly-greater weight replaces, first-seen position kept."""
+    m = e["src"].shape[0]
+    if m == 0:
+        return e
+    a, b = np.minimum(e["src"], e["tgt"]), np.maximum(e["src"], e["tgt"])
+    key = a * np.int64(n) + b
+    order = np.arange(m)
+    # winner per key: max weight, earliest among equals; position: first occurrence of the key
+    srt = np.lexsort((order, -e["weight"], key))
+    ks = key[srt]
+    first_of_group = np.ones(m, bool)
+    first_of_group[1:] = ks[1:] != ks[:-1]
+    winners = srt[first_of_group]
+    _, first_pos = np.unique(key, return_index=True)            # sorted by key, like ks[first_of_group]
+    emit = winners[np.argsort(first_pos, kind="stable")]
+    return {k: v[emit] for k, v in e.items()}
+
+
+class TissueGraphBuilder:
+    """Same constructor as the reference (:50-59). The ImageNet/DINOv2 patch feature extractor of the reference
+    (timm, network download, :85-137) is outside the hot path: patches must carry `features` (or fall back to the
+    reference's 5 metadata placeholders)."""
+
+    def __init__(self, feature_extractor="dinov2", spatial_k=8, morphological_k=16, edge_threshold=0.7,
+                 hierarchical_levels=3, min_component_size=5, use_adaptive_threshold=True, device=None):
+        self.feature_extractor = feature_extractor
+        self.spatial_k, self.morphological_k, self.edge_threshold = spatial_k, morphological_k, edge_threshold
+        self.hierarchical_levels, self.min_component_size = hierarchical_levels, min_component_size
+        self.use_adaptive_threshold = use_adaptive_threshold
+        self.logger = logging.getLogger(__name__)
+        self.feature_dim = 768 if feature_extractor == "dinov2" else 512
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device()) \
+            if torch.cuda.is_available() else None
+
+    # ---------------------------------------------------------------------------------- nodes
+    def _create_placeholder_features(self, patch):
+        f = np.array([patch.tissue_percentage, patch.magnification / 40.0, float(patch.level),
+                      np.log1p(patch.x / 1000.0), np.log1p(patch.y / 1000.0)])
+        if len(f) < self.feature_dim:
+            f = np.concatenate([f, np.zeros(self.feature_dim - len(f))])
+        return f[:self.feature_dim]
+
+    def _normalize_coordinates(self, x, y, metadata):
+        if "dimensions" in metadata:
+            w, h = metadata["dimensions"]
+            return (x / w, y / h)
+        return (x / 50000.0, y / 50000.0)
+
+    def _create_nodes(self, slide_data, patch_images=None):
+        if patch_images:
+            raise NotImplementedError("patch image feature extraction (timm / CNN) is outside the B200 hot path; "
+                                      "supply PatchInfo.features")
+        nodes = []
+        for p in slide_data.patches:
+            f = p.features if p.features is not None else self._create_placeholder_features(p)
+            nodes.append(GraphNode(p.patch_id, p, f, self._normalize_coordinates(p.x, p.y, slide_data.metadata)))
+        return nodes
+
+    # ---------------------------------------------------------------------------------- edges
+    def edge_arrays(self, features, coords):
+        """features float [n,d], coords float64 [n,2] (numpy). Returns the de-duplicated edge arrays in emission order."""
+        if self.device is None:
+            raise KernelError("TissueGraphBuilder needs a CUDA (B200) device; there is no CPU fallback")
+        n = features.shape[0]
+        f = torch.as_tensor(np.ascontiguousarray(features, dtype=np.float32)).to(self.device)
+        c = torch.as_tensor(np.ascontiguousarray(coords, dtype=np.float64)).to(self.device)
+        ks, km = min(self.spatial_k + 1, n), min(self.morphological_k + 1, n)
+        sp_idx, sp_dist = knn2d(c, ks)
+        mo_idx, mo_cos, _ = knn_cosine(f, km)
+        e = candidate_edges(sp_idx.cpu().numpy(), sp_dist.cpu().numpy(), mo_idx.cpu().numpy(), mo_cos.cpu().numpy(),
+                            self.edge_threshold)
+        return remove_duplicate_edges(e, n)
+
+    def build_graph(self, slide_data, patch_images=None):
+        nodes = self._create_nodes(slide_data, patch_images)
+        if len(nodes) == 0:
+            return self._create_empty_graph()
+        ids = [nd.node_id for nd in nodes]
+        if len(set(ids)) != len(ids):
+            raise ValueError("patch ids must be unique")
+        feats = np.stack([nd.features for nd in nodes])
+        coords = np.array([nd.spatial_coords for nd in nodes], dtype=np.float64)
+        e = self.edge_arrays(feats, coords)
+        m = e["src"].shape[0]
+        x = torch.tensor(feats, dtype=torch.float)
+        pos = torch.tensor(coords, dtype=torch.float)
+        if m > 0:
+            ei = np.empty((2, 2 * m), dtype=np.int64)
+            ei[0, 0::2], ei[1, 0::2] = e["src"], e["tgt"]                # (s,t) then (t,s), :400
+            ei[0, 1::2], ei[1, 1::2] = e["tgt"], e["src"]
+            attr = np.repeat(np.stack([e["f0"], e["f1"]], axis=1), 2, axis=0)
+            et = np.repeat(e["type"], 2)
+            edge_index, edge_attr, edge_type = torch.tensor(ei), torch.tensor(attr, dtype=torch.float), torch.tensor(et)
+        else:
+            edge_index = torch.empty((2, 0), dtype=torch.long)
+            edge_attr = torch.empty((0, 1), dtype=torch.float)
+            edge_type = torch.empty((0,), dtype=torch.long)
+        data = Data(x=x, edge_index=edge_index, edge_attr=edge_attr, pos=pos, edge_type=edge_type, num_nodes=len(nodes))
+        data.slide_id = slide_data.slide_id
+        data.num_patches = len(slide_data.patches)
+        data.slide_metadata = slide_data.metadata
+        return data
+
+    def _create_empty_graph(self):
+        return Data(x=torch.empty((0, self.feature_dim), dtype=torch.float), edge_index=torch.empty((2, 0), dtype=torch.long),
+                    edge_attr=torch.empty((0, 1), dtype=torch.float), pos=torch.empty((0, 2), dtype=torch.float), num_nodes=0)

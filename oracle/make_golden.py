@@ -1,0 +1,152 @@
+"""TEST INFRASTRUCTURE — generates tests/golden/*.npz by running the REAL reference (oracle/ref_loader.py: verbatim
+files from /root/reference + patch set P1-P7) in the build container. The fixtures travel to the GPU box, the
+reference does not.  Run:  python -m oracle.make_golden
+
+Inputs and weights are regenerated from seeds by dgdm_histopath_lab_b200.synth (not stored); only reference OUTPUTS
+(and the few injected random draws) are stored.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader                                            # noqa: E402
+from dgdm_histopath_lab_b200 import synth                                # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+SMALL_CFG = dict(node_features=48, hidden_dims=[64, 32, 32], num_diffusion_steps=10, attention_heads=2, graph_layers=4,
+                 num_classes=3, regression_targets=2)
+BASE_CFG = dict(node_features=768, hidden_dims=[512, 256, 128], num_diffusion_steps=10, attention_heads=8, graph_layers=4)
+
+
+def _to_ref(ns, d):
+    out = ns["Data"](x=d.x, edge_index=d.edge_index, edge_attr=d.edge_attr, pos=d.pos)
+    if getattr(d, "batch", None) is not None:
+        b = ns["Batch"](x=d.x, edge_index=d.edge_index, edge_attr=d.edge_attr, pos=d.pos)
+        b.batch = d.batch
+        return b
+    return out
+
+
+def ref_model(ns, cfg, seed=0):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = ns["DGDMModel"](**cfg).eval()
+    m.load_state_dict(synth.seeded_state_dict(m, seed))
+    return m
+
+
+def small_batch():
+    return synth.tile_batch(2, 150, SMALL_CFG["node_features"], seed=11)
+
+
+def pretrain_draws(seed, sizes, dim, steps):
+    """Replays the order of torch RNG calls in DGDMModel._compute_diffusion_loss (models/dgdm_model.py:411-429)."""
+    torch.manual_seed(seed)
+    t = torch.randint(0, steps, (len(sizes),))
+    noise, target = [], []
+    for n in sizes:
+        noise.append(torch.randn(1, n, dim)[0])
+        target.append(torch.randn(n, dim))
+    return t, noise, target
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    ns = ref_loader.load()
+    torch.set_num_threads(8)
+
+    # ---- 1. small model, 2-graph batch: inference (+ stages via hooks) and pretrain with replayed RNG
+    m = ref_model(ns, SMALL_CFG)
+    b = small_batch()
+    rb = _to_ref(ns, b)
+    stages = {}
+    hooks = [m.feature_encoder.register_forward_hook(lambda mod, i, o: stages.__setitem__("feature_encoder", o.detach().clone())),
+             m.graph_encoder.register_forward_hook(lambda mod, i, o: stages.__setitem__("graph_encoder", o["embeddings"].detach().clone())),
+             m.hierarchical_processor.register_forward_hook(lambda mod, i, o: stages.__setitem__("unet", o.detach().clone()))]
+    with torch.no_grad():
+        out = m(rb, return_embeddings=True, return_attention=True)
+    for h in hooks:
+        h.remove()
+    torch.manual_seed(77)
+    with torch.no_grad():
+        outp = m(rb, mode="pretrain")
+    np.savez_compressed(os.path.join(GOLDEN, "small_model.npz"),
+                        node_embeddings=out["node_embeddings"].numpy(), graph_embedding=out["graph_embedding"].numpy(),
+                        classification_logits=out["classification_logits"].numpy(),
+                        regression_outputs=out["regression_outputs"].numpy(),
+                        attention0=out["attention_weights"][0].numpy(), attention1=out["attention_weights"][1].numpy(),
+                        feature_encoder=stages["feature_encoder"].numpy(), graph_encoder=stages["graph_encoder"].numpy(),
+                        unet=stages["unet"].numpy(),
+                        pretrain_seed=np.int64(77), diffusion_loss=outp["diffusion_loss"].numpy(),
+                        noisy_embeddings=outp["noisy_embeddings"].numpy(),
+                        state_keys=np.array(sorted(m.state_dict().keys())))
+    print("small_model: nodes", b.x.shape, "loss", float(outp["diffusion_loss"]))
+
+    # ---- 2. small model with 32-d edge attributes through the encoder only (GraphUNet+edge_attr pooling is not in the product yet)
+    g = torch.Generator().manual_seed(5)
+    ea = torch.randn(b.edge_index.size(1), 32, generator=g)
+    with torch.no_grad():
+        enc = m.graph_encoder(m.feature_encoder(b.x), b.edge_index, ea, b.batch)["embeddings"]
+        dyn = m.graph_encoder.graph_layers[1].compute_dynamic_edges(stages["feature_encoder"], b.edge_index, ea)
+    np.savez_compressed(os.path.join(GOLDEN, "small_edge_attr.npz"), graph_encoder=enc.numpy(), dynamic_edges=dyn.numpy())
+
+    # ---- 3. module-level: diffusion forward / sample, pooling
+    torch.manual_seed(3)
+    x0 = torch.randn(200, 32)
+    t = torch.full((200,), 4, dtype=torch.long)
+    noise = torch.randn(200, 32)
+    with torch.no_grad():
+        xn, eps = m.diffusion_layer(x0, t, noise)
+        init = torch.randn(40, 32)
+        steps = [torch.randn(40, 32) for _ in range(5)]
+        torch.manual_seed(9)
+        # replay: sample() draws randn(shape) then randn_like per non-final step
+        samp_seeded = m.diffusion_layer.sample((40, 32), torch.device("cpu"), num_inference_steps=6)
+        torch.manual_seed(9)
+        init9 = torch.randn(40, 32)
+        steps9 = [torch.randn(40, 32) for _ in range(5)]
+        px, pei, _, perm = m.hierarchical_processor.pools[0](stages["graph_encoder"], b.edge_index)
+    np.savez_compressed(os.path.join(GOLDEN, "modules.npz"), x0=x0.numpy(), noise=noise.numpy(), x_noisy=xn.numpy(), eps=eps.numpy(),
+                        sample_init=init9.numpy(), sample_steps=np.stack([s.numpy() for s in steps9]), sample_out=samp_seeded.numpy(),
+                        pool_x=px.numpy(), pool_ei=pei.numpy(), pool_perm=perm.numpy())
+
+    # ---- 4. DGDM-Base (configs/dgdm_base.yaml) on the config-1 graph: N=2000, E~32000
+    mb = ref_model(ns, BASE_CFG)
+    d = synth.tile_graph(2000, 768, seed=1234)
+    st = {}
+    hooks = [mb.graph_encoder.register_forward_hook(lambda mod, i, o: st.__setitem__("graph_encoder", o["embeddings"].detach().clone())),
+             mb.spatial_attention.register_forward_hook(lambda mod, i, o: st.__setitem__("spatial", o[0].detach().clone()))]
+    with torch.no_grad():
+        ob = mb(_to_ref(ns, d), return_embeddings=True)
+    for h in hooks:
+        h.remove()
+    np.savez_compressed(os.path.join(GOLDEN, "base_2k.npz"), node_embeddings=ob["node_embeddings"].numpy(),
+                        graph_embedding=ob["graph_embedding"].numpy(), graph_encoder=st["graph_encoder"].numpy()[::8],
+                        spatial=st["spatial"][0].numpy()[::8], num_params=np.int64(sum(p.numel() for p in mb.parameters())))
+    print("base_2k: E", d.edge_index.shape, "params", sum(p.numel() for p in mb.parameters()))
+
+    # ---- 5. builder: 600 patches, 64-d clustered features, jittered grid
+    n = 600
+    feats = synth.clustered_features(n, d=64, num_clusters=12, seed=21, sigma_lo=0.05, sigma_hi=0.11)
+    xs, ys, dims = synth.jittered_grid_coords(n, seed=21, extent=3000)
+    sp = ns["sp"]
+    patches = [sp.PatchInfo(int(xs[i]), int(ys[i]), 0, 20.0, f"s_patch_{i:06d}", 0.9, feats[i]) for i in range(n)]
+    slide = sp.SlideData("s", patches, {"dimensions": dims})
+    tb = ns["TissueGraphBuilder"].__new__(ns["TissueGraphBuilder"])
+    tb.__dict__.update(dict(feature_extractor="none", spatial_k=8, morphological_k=16, edge_threshold=0.7, hierarchical_levels=3,
+                            min_component_size=5, use_adaptive_threshold=True, feature_dim=64))
+    import logging
+    tb.logger = logging.getLogger("golden")
+    gph = tb.build_graph(slide)
+    np.savez_compressed(os.path.join(GOLDEN, "builder_600.npz"), edge_index=gph.edge_index.numpy(), edge_attr=gph.edge_attr.numpy(),
+                        edge_type=gph.edge_type.numpy(), pos=gph.pos.numpy())
+    print("builder_600: edges", gph.edge_index.shape, "types", np.bincount(gph.edge_type.numpy()))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,222 @@
+"""GPU parity tests, kernel by kernel, through the C-ABI (ops.py -> libdgdm_b200.so) against the CPU oracle
+(oracle/dgdm_oracle.py) or an fp64 torch restatement of the same op, on the same seeded inputs.
+Tolerances: fp32 path rel 1e-5 per op (split-fp16 tensor products are fp32-class); index work bit-exact."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from dgdm_histopath_lab_b200 import ops, synth
+from dgdm_histopath_lab_b200.graph import GraphContext
+from oracle import dgdm_oracle as O
+from util import SMALL_CFG, golden, make_model, rel_err, sd_cpu
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+# ------------------------------------------------------------------------------------------ structure (exact)
+def test_csr_build_exact_order_and_norm():
+    d = synth.tile_graph(3000, 8, seed=3)
+    ei = d.edge_index
+    n = 3000
+    csr = ops.csr_build(ei.to(DEV), n)
+    order = torch.sort(ei[1], stable=True)[1]
+    rowptr = F.pad(torch.cumsum(torch.bincount(ei[1], minlength=n), 0), (1, 0))
+    assert torch.equal(csr.rowptr.cpu().long(), rowptr)
+    assert torch.equal(csr.eid.cpu().long(), order)
+    assert torch.equal(csr.col.cpu().long(), ei[0][order])
+    _, norm = O.gcn_norm(ei, n)
+    assert torch.equal(csr.norm.cpu(), norm[:ei.size(1)][order])          # bit-exact deg^-1/2 products
+
+
+def test_csr_isolated_nodes_multi_edges_self_loops():
+    ei = torch.tensor([[0, 0, 2, 2, 2, 5, 5], [1, 1, 2, 0, 0, 5, 0]])
+    csr = ops.csr_build(ei.to(DEV), 7)
+    assert csr.rowptr.cpu().tolist() == [0, 3, 5, 6, 6, 6, 7, 7]
+    x = torch.randn(7, 16, generator=_gen(0))
+    w = torch.eye(16)
+    ref = O.graph_convolution({"c.node_lin.weight": w}, "c", x, ei)
+    out = ops.spmm_gcn(csr, x.to(DEV))
+    assert rel_err(out, ref)[0] < 1e-6
+
+
+@pytest.mark.parametrize("C", [16, 128, 256, 512, 768])
+def test_spmm_gcn_vs_oracle(C):
+    d = synth.tile_graph(2500, 8, seed=4)
+    x = torch.randn(2500, C, generator=_gen(C))
+    bias = torch.randn(C, generator=_gen(C + 1)) * 0.1
+    ref = F.gelu(O.graph_convolution({"c.node_lin.weight": torch.eye(C), "c.bias": bias}, "c", x, d.edge_index))
+    csr = ops.csr_build(d.edge_index.to(DEV), 2500)
+    out = ops.spmm_gcn(csr, x.to(DEV), bias=bias.to(DEV), act="gelu")
+    assert rel_err(out, ref)[0] < 2e-6
+    out2 = ops.spmm_gcn(csr, x.to(DEV), bias=bias.to(DEV), act="gelu")
+    assert torch.equal(out, out2), "SpMM must be bitwise deterministic"
+
+
+def test_topk_pool_exact_vs_oracle():
+    m = make_model(SMALL_CFG)
+    sd = sd_cpu(m)
+    x = torch.tensor(golden("small_model.npz")["graph_encoder"])
+    b = synth.tile_batch(2, 150, 48, seed=11)
+    px, pei, _, perm, s = O.adaptive_graph_pooling(sd, "hierarchical_processor.pools.0", x, b.edge_index)
+    perm_g, node_map = ops.topk_select(s.to(DEV), perm.numel())
+    assert torch.equal(perm_g.cpu().long(), perm)
+    csr = ops.csr_build(b.edge_index.to(DEV), 300)
+    pc = ops.csr_pool(csr, perm_g, node_map)
+    ref = ops.csr_build(pei.to(DEV), perm.numel())
+    e = int(ref.rowptr[-1])
+    assert torch.equal(pc.rowptr, ref.rowptr) and torch.equal(pc.col[:e], ref.col[:e]) and torch.equal(pc.norm[:e], ref.norm[:e])
+    g = ops.pool_gather(x.to(DEV), s.to(DEV), perm_g)
+    assert rel_err(g, px)[0] < 1e-6
+
+
+def test_topk_ties_lowest_index_first():
+    s = torch.tensor([0.5, 0.9, 0.5, 0.5, 0.1, 0.9, 0.5, -0.3])
+    perm, nm = ops.topk_select(s.to(DEV), 4)
+    assert perm.cpu().tolist() == [0, 1, 2, 5]
+    assert nm.cpu().tolist() == [0, 1, 2, -1, -1, 3, -1, -1]
+
+
+def test_unpool_add_act():
+    skip = torch.randn(50, 32, generator=_gen(1)); x = torch.randn(20, 32, generator=_gen(2))
+    perm = torch.sort(torch.randperm(50, generator=_gen(3))[:20])[0]
+    nm = torch.full((50,), -1, dtype=torch.int32); nm[perm] = torch.arange(20, dtype=torch.int32)
+    up = torch.zeros(50, 32); up[perm] = x
+    out = ops.unpool_add_act(skip.to(DEV), x.to(DEV), nm.to(DEV), act="relu")
+    assert torch.equal(out.cpu(), F.relu(up + skip))
+
+
+# ------------------------------------------------------------------------------------------ GEMM (tcgen05)
+def _ref_linear(a, w, bias, r_pre, act_pre, ln1, ln2, act_post, r_post):
+    acts = {None: lambda v: v, "gelu": F.gelu, "relu": F.relu, "silu": F.silu, "tanh": torch.tanh}
+    v = a.double() @ w.double().t()
+    if bias is not None: v = v + bias.double()
+    if r_pre is not None: v = v + r_pre.double()
+    v = acts[act_pre](v)
+    for ln in (ln1, ln2):
+        if ln is not None: v = F.layer_norm(v, (v.size(1),), ln[0].double(), ln[1].double(), 1e-5)
+    v = acts[act_post](v)
+    if r_post is not None: v = v + r_post.double()
+    return v
+
+
+@pytest.mark.parametrize("mode", ["tc", "simt"])
+@pytest.mark.parametrize("M,K,N", [(300, 128, 128), (1000, 768, 512), (257, 32, 64), (128, 512, 384), (77, 128, 16), (4, 256, 256)])
+def test_linear_plain(mode, M, K, N):
+    a = torch.randn(M, K, generator=_gen(M + K)); w = torch.randn(N, K, generator=_gen(N)) / K ** 0.5
+    out = ops.linear(a.to(DEV), ops.SplitWeight(w.to(DEV)), mode=mode)
+    assert rel_err(out, a.double() @ w.double().t())[0] < 3e-6
+
+
+@pytest.mark.parametrize("N", [64, 128, 512])
+def test_linear_fused_epilogues(N):
+    M, K = 333, 256
+    g = _gen(N)
+    a = torch.randn(M, K, generator=g); w = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g) * 0.3; r1 = torch.randn(M, N, generator=g); r2 = torch.randn(M, N, generator=g)
+    ln1 = (1 + 0.1 * torch.randn(N, generator=g), 0.1 * torch.randn(N, generator=g))
+    ln2 = (1 + 0.1 * torch.randn(N, generator=g), 0.1 * torch.randn(N, generator=g))
+    W = ops.SplitWeight(w.to(DEV))
+    c = lambda t: None if t is None else (tuple(x.to(DEV) for x in t) if isinstance(t, tuple) else t.to(DEV))
+    cases = [dict(bias=bias, act_post="gelu"), dict(bias=bias, r_pre=r1, ln1=ln1), dict(bias=bias, r_pre=r1, ln1=ln1, ln2=ln2, act_post="gelu"),
+             dict(bias=bias, ln1=ln1, act_post="gelu", r_post=r2), dict(act_pre="relu", bias=bias), dict(bias=bias, ln2=ln2, act_post="silu")]
+    for kw in cases:
+        ref = _ref_linear(a, w, kw.get("bias"), kw.get("r_pre"), kw.get("act_pre"), kw.get("ln1"), kw.get("ln2"), kw.get("act_post"), kw.get("r_post"))
+        out = ops.linear(a.to(DEV), W, c(kw.get("bias")), r_pre=c(kw.get("r_pre")), act_pre=kw.get("act_pre"), ln1=c(kw.get("ln1")),
+                         ln2=c(kw.get("ln2")), act_post=kw.get("act_post"), r_post=c(kw.get("r_post")))
+        assert rel_err(out, ref)[0] < 5e-6, kw.keys()
+
+
+def test_linear_rowdot_and_rowbias_and_wide():
+    g = _gen(5)
+    a = torch.randn(500, 128, generator=g); w = torch.randn(64, 128, generator=g) / 11; b = torch.randn(64, generator=g) * 0.1
+    dw = torch.randn(64, generator=g) / 8
+    _, s = ops.linear(a.to(DEV), ops.SplitWeight(w.to(DEV)), b.to(DEV), act_post="relu", want_out=False, dot=(dw.to(DEV), 0.05, "tanh"))
+    ref = torch.tanh(F.relu(a.double() @ w.double().t() + b.double()) @ dw.double() + 0.05)
+    assert rel_err(s, ref)[0] < 3e-6
+    tab = torch.randn(3, 64, generator=g); idx = torch.randint(0, 3, (500,), generator=g).int()
+    out = ops.linear(a.to(DEV), ops.SplitWeight(w.to(DEV)), None, row_bias=(idx.to(DEV), tab.to(DEV)))
+    assert rel_err(out, a.double() @ w.double().t() + tab.double()[idx.long()])[0] < 3e-6
+    w2 = torch.randn(768, 128, generator=g) / 11; ln = (1 + 0.1 * torch.randn(768, generator=g), 0.1 * torch.randn(768, generator=g))
+    out = ops.linear(a.to(DEV), ops.SplitWeight(w2.to(DEV)), None, ln1=(ln[0].to(DEV), ln[1].to(DEV)), act_post="gelu")
+    assert rel_err(out, _ref_linear(a, w2, None, None, None, ln, None, "gelu", None))[0] < 5e-6
+
+
+# ------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("precise,tol", [(1, 2e-5), (0, 2e-3)])
+def test_spatial_attention_core_vs_dense(precise, tol):
+    g = _gen(9)
+    segs = [0, 333, 1000]; n, D, H = 1000, 128, 8
+    qkv = torch.randn(n, 3 * D, generator=g); pos = torch.rand(n, 2, generator=g)
+    refs = []
+    for a, b in zip(segs[:-1], segs[1:]):
+        q, k, v = (qkv[a:b, i * D:(i + 1) * D].double().view(b - a, H, 16).transpose(0, 1) for i in range(3))
+        bias = -torch.cdist(pos[a:b].double(), pos[a:b].double())
+        w = torch.softmax(q @ k.transpose(1, 2) / 4.0 + bias, dim=-1)
+        refs.append((w @ v).transpose(0, 1).reshape(b - a, D))
+    ref = torch.cat(refs)
+    seg = torch.tensor(segs, dtype=torch.int32, device=DEV)
+    out = ops.spatial_attention(qkv.to(DEV), pos.to(DEV), seg, 2, H, 1.0, precise=precise)
+    assert rel_err(out, ref)[0] < tol
+    w = ops.spatial_attention_weights(qkv[:333].to(DEV), pos[:333].to(DEV), H)
+    q, k = (qkv[:333, i * D:(i + 1) * D].double().view(333, H, 16).transpose(0, 1) for i in range(2))
+    wref = torch.softmax(q @ k.transpose(1, 2) / 4.0 - torch.cdist(pos[:333].double(), pos[:333].double()), -1).mean(0)
+    assert rel_err(w, wref)[0] < 1e-5
+
+
+def test_spatial_attention_large_scores_trigger_rescale():
+    g = _gen(10)
+    n, D, H = 700, 128, 8
+    qkv = torch.randn(n, 3 * D, generator=g) * 3.0            # scores with std ~9: exercises the lazy-max refresh path
+    pos = torch.rand(n, 2, generator=g)
+    q, k, v = (qkv[:, i * D:(i + 1) * D].double().view(n, H, 16).transpose(0, 1) for i in range(3))
+    ref = (torch.softmax(q @ k.transpose(1, 2) / 4.0 - torch.cdist(pos.double(), pos.double()), -1) @ v).transpose(0, 1).reshape(n, D)
+    seg = torch.tensor([0, n], dtype=torch.int32, device=DEV)
+    out = ops.spatial_attention(qkv.to(DEV), pos.to(DEV), seg, 1, H, 1.0, precise=1)
+    assert rel_err(out, ref)[0] < 5e-5
+
+
+def test_attention_pool_vs_oracle():
+    m = make_model(SMALL_CFG); sd = sd_cpu(m)
+    x = torch.randn(300, 32, generator=_gen(2)); batch = torch.cat([torch.zeros(120), torch.ones(180)]).long()
+    ref = O.global_attention_pool(sd, "global_pool", x, batch, 2)
+    mg = m.to(DEV)
+    seg = torch.tensor([0, 120, 300], dtype=torch.int32, device=DEV)
+    out = mg.global_pool(x.to(DEV), seg_ptr=seg, num_seg=2)
+    assert rel_err(out, ref)[0] < 1e-5
+
+
+def test_spatial_pe_matches_oracle():
+    pos = torch.rand(200, 2, generator=_gen(4)) * 3 - 1
+    x = torch.randn(200, 128, generator=_gen(5))
+    seg = torch.tensor([0, 80, 200], dtype=torch.int32, device=DEV)
+    out = ops.spatial_pe_add(x.to(DEV), pos.to(DEV), seg, 2)
+    ref = torch.cat([x[:80] + O.spatial_positional_encoding(pos[:80], 128), x[80:] + O.spatial_positional_encoding(pos[80:], 128)])
+    assert rel_err(out, ref)[0] < 2e-6
+
+
+# ------------------------------------------------------------------------------------------ diffusion / dynamic edges
+def test_diffusion_forward_and_sample_vs_golden_and_oracle():
+    g = golden("modules.npz")
+    m = make_model(SMALL_CFG).to(DEV)
+    t = torch.full((200,), 4, dtype=torch.long, device=DEV)
+    xn, eps = m.diffusion_layer(torch.tensor(g["x0"]).to(DEV), t, torch.tensor(g["noise"]).to(DEV))
+    assert rel_err(xn, g["x_noisy"])[0] < 1e-6 and rel_err(eps, g["eps"])[0] < 2e-5
+    s = m.diffusion_layer.sample((40, 32), torch.device(DEV), num_inference_steps=6, init=torch.tensor(g["sample_init"]),
+                                 step_noise=torch.tensor(g["sample_steps"]))
+    assert rel_err(s, g["sample_out"])[0] < 1e-4
+
+
+def test_compute_dynamic_edges_vs_golden():
+    g = golden("small_edge_attr.npz"); gm = golden("small_model.npz")
+    m = make_model(SMALL_CFG).to(DEV)
+    b = synth.tile_batch(2, 150, 48, seed=11)
+    ea = torch.randn(b.edge_index.size(1), 32, generator=_gen(5))
+    layer = m.graph_encoder.graph_layers[1]
+    out = layer.compute_dynamic_edges(torch.tensor(gm["feature_encoder"]).to(DEV), b.edge_index.to(DEV), ea.to(DEV))
+    assert rel_err(out, g["dynamic_edges"])[0] < 2e-5

@@ -1,0 +1,108 @@
+"""GPU end-to-end parity: DGDMModel.forward (CUDA kernels through the C-ABI) against the CPU oracle on identical seeded
+weights and graphs, and against the golden vectors recorded from the real reference.
+Tolerance: rel 1e-4 (north_star fp32-path bar) on node embeddings / graph embeddings. Top-k pooling is discontinuous, so
+`perm` sets are compared first and flips are reported (SURVEY.md §7 "hard parts")."""
+import numpy as np
+import pytest
+import torch
+
+from dgdm_histopath_lab_b200 import Batch, Data, ModelInferenceError, synth
+from oracle import builder_oracle, dgdm_oracle as O
+from util import BASE_CFG, SMALL_CFG, golden, make_model, oracle_cfg, pretrain_draws, rel_err, sd_cpu
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_small_batch_forward_vs_golden_and_oracle():
+    g = golden("small_model.npz")
+    m = make_model(SMALL_CFG).to(DEV)
+    b = synth.tile_batch(2, 150, 48, seed=11).to(DEV)
+    out = m(b, return_embeddings=True, return_attention=True)
+    assert rel_err(out["node_embeddings"], g["node_embeddings"])[0] < 1e-4
+    assert rel_err(out["graph_embedding"], g["graph_embedding"])[0] < 1e-4
+    assert rel_err(out["classification_logits"], g["classification_logits"])[0] < 1e-4
+    assert rel_err(out["regression_outputs"], g["regression_outputs"])[0] < 1e-4
+    assert rel_err(out["attention_weights"][0], g["attention0"])[0] < 1e-4
+    assert rel_err(out["attention_weights"][1], g["attention1"])[0] < 1e-4
+    assert abs(float(out["classification_probs"].sum(-1)[0]) - 1.0) < 1e-5
+    out2 = m(b, return_embeddings=True)
+    assert torch.equal(out["node_embeddings"], out2["node_embeddings"]), "forward must be bitwise deterministic"
+
+
+def test_small_pretrain_vs_golden():
+    g = golden("small_model.npz")
+    m = make_model(SMALL_CFG).to(DEV)
+    b = synth.tile_batch(2, 150, 48, seed=11).to(DEV)
+    t, noise, target = pretrain_draws(int(g["pretrain_seed"]), [150, 150], 32, 10)
+    out = m(b, mode="pretrain", rng=dict(timesteps=t, noise=torch.cat(noise), target=torch.cat(target)))
+    assert abs(float(out["diffusion_loss"]) - float(g["diffusion_loss"])) < 1e-4 * abs(float(g["diffusion_loss"]))
+    assert rel_err(out["noisy_embeddings"], g["noisy_embeddings"])[0] < 1e-4
+    assert "classification_logits" not in out
+
+
+def test_encoder_with_edge_attr_vs_golden():
+    g = golden("small_edge_attr.npz")
+    m = make_model(SMALL_CFG).to(DEV)
+    b = synth.tile_batch(2, 150, 48, seed=11)
+    ea = torch.randn(b.edge_index.size(1), 32, generator=torch.Generator().manual_seed(5))
+    h = m.feature_encoder(b.x.to(DEV))
+    enc = m.graph_encoder(h, b.edge_index.to(DEV), ea.to(DEV))["embeddings"]
+    assert rel_err(enc, g["graph_encoder"])[0] < 2e-5
+
+
+def test_base_config1_2k_nodes_vs_golden():
+    """BASELINE.json configs[0]: DGDM-Base forward on one 2k-node tile graph vs the reference's own output."""
+    g = golden("base_2k.npz")
+    m = make_model(BASE_CFG).to(DEV)
+    d = synth.tile_graph(2000, 768, seed=1234).to(DEV)
+    out = m(d, return_embeddings=True)
+    mx, row = rel_err(out["node_embeddings"], g["node_embeddings"])
+    print("base_2k node_embeddings rel err: max-scaled", mx, "row-L2", row)
+    assert mx < 1e-4
+    assert rel_err(out["graph_embedding"], g["graph_embedding"])[0] < 1e-4
+
+
+def test_single_graph_without_pos_or_batch_and_unet_perms():
+    m = make_model(SMALL_CFG)
+    d = synth.tile_graph(257, 48, seed=5)
+    ref = O.dgdm_forward(sd_cpu(m), oracle_cfg(SMALL_CFG), d.x, d.edge_index, None, None, None, return_stages=True)
+    mg = m.to(DEV)
+    dd = Data(x=d.x.to(DEV), edge_index=d.edge_index.to(DEV))
+    out = mg(dd, return_embeddings=True)
+    assert rel_err(out["node_embeddings"], ref["node_embeddings"])[0] < 1e-4
+    _, perms = mg.hierarchical_processor(ref["stages"]["spatial_attention"].to(DEV), dd.edge_index, return_perms=True)
+    flips = sum(int((set(p.cpu().tolist()) ^ set(q.tolist())) != set()) for p, q in zip(perms, ref["stages"]["perms"]))
+    assert flips == 0, f"top-k selection flipped in {flips} pooling levels"
+
+
+def test_error_contract_on_device():
+    m = make_model(SMALL_CFG).to(DEV)
+    d = synth.tile_graph(64, 48, seed=1).to(DEV)
+    bad = d.clone(); bad.x[3, 4] = float("nan")
+    with pytest.raises(ModelInferenceError, match="NaN"):
+        m(bad)
+    bad = d.clone(); bad.edge_index[0, 0] = 64
+    with pytest.raises(ModelInferenceError, match="invalid node indices"):
+        m(bad)
+    with pytest.raises(ModelInferenceError):
+        m(Data(x=torch.randn(64, 47, device=DEV), edge_index=d.edge_index))
+    with pytest.raises(ModelInferenceError):
+        m(Data())
+    with pytest.raises(ModelInferenceError):
+        m(d, mode="bogus")
+
+
+def test_builder_edges_exact_vs_golden_and_oracle():
+    from dgdm_histopath_lab_b200 import PatchInfo, SlideData, TissueGraphBuilder
+    g = golden("builder_600.npz")
+    n = 600
+    feats = synth.clustered_features(n, d=64, num_clusters=12, seed=21, sigma_lo=0.05, sigma_hi=0.11)
+    xs, ys, dims = synth.jittered_grid_coords(n, seed=21, extent=3000)
+    patches = [PatchInfo(int(xs[i]), int(ys[i]), 0, 20.0, f"s_patch_{i:06d}", 0.9, feats[i]) for i in range(n)]
+    tb = TissueGraphBuilder(feature_extractor="none")
+    gph = tb.build_graph(SlideData("s", patches, {"dimensions": dims}))
+    assert np.array_equal(gph.edge_index.numpy(), g["edge_index"]), "edge list must match the reference exactly (indices and order)"
+    assert np.array_equal(gph.edge_type.numpy(), g["edge_type"])
+    assert np.allclose(gph.edge_attr.numpy(), g["edge_attr"], rtol=0, atol=2e-7)
+    assert np.array_equal(gph.pos.numpy(), g["pos"])

@@ -1,0 +1,258 @@
+#!/usr/bin/env python
+"""bench.py — DGDM-Base forward nodes/sec on a synthetic 100k-node, 768-d, ~16-degree tile graph (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference ...                     the reference's CPU implementation of the path (oracle port of the
+                                                           patched reference; the unpatched reference forward raises for every input)
+
+One JSON line on rank 0. `value`: inputs resident in HBM, K forwards timed with CUDA events, max over ranks.
+`e2e`: same metric through the public API with pinned HOST buffers (H2D of x/edge_index/pos and D2H of the graph
+embedding inside the timed region, CSR rebuilt every step because the inputs are new tensors).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BASE_CFG = dict(node_features=768, hidden_dims=[512, 256, 128], num_diffusion_steps=10, attention_heads=8, graph_layers=4)
+METRIC = "DGDM fwd nodes/sec (100k-node graph)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    def __init__(self, dev):
+        self.dev, self.rows, self._stop, self._t = dev, [], threading.Event(), None
+
+    def start(self):
+        def run():
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            while not self._stop.is_set():
+                try:
+                    o = subprocess.run(["nvidia-smi", f"--id={self.dev}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                       capture_output=True, text=True, timeout=5).stdout.strip()
+                    if o:
+                        self.rows.append([c.strip() for c in o.split(",")])
+                except Exception:
+                    pass
+                self._stop.wait(0.2)
+        self._t = threading.Thread(target=run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+
+
+def oracle_nodes_per_sec(n_nodes, reps, threads=None):
+    """CPU baseline: oracle port (oracle/dgdm_oracle.py) of the patched reference forward on an n_nodes tile graph."""
+    from dgdm_histopath_lab_b200 import DGDMModel, synth
+    from oracle import dgdm_oracle as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = DGDMModel(**BASE_CFG).eval()
+    sd = synth.seeded_state_dict(m, 0)
+    d = synth.tile_graph(n_nodes, 768, seed=1234)
+    cfg = dict(hidden_dims=BASE_CFG["hidden_dims"], attention_heads=8, graph_layers=4)
+    times = []
+    with torch.no_grad():
+        O.dgdm_forward(sd, cfg, d.x, d.edge_index, None, None, d.pos)
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            O.dgdm_forward(sd, cfg, d.x, d.edge_index, None, None, d.pos)
+            times.append(time.perf_counter() - t0)
+    return n_nodes / min(times), threads, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.ref_nodes
+    t0 = time.perf_counter()
+    v, threads, times = oracle_nodes_per_sec(n, max(1, args.steps))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "nodes/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * min(times), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"DGDM-Base forward, one {n}-node 768-d ~16-degree tile graph (bounded sample of the 100k-node workload: "
+                                   f"the reference's dense N x N attention needs 320 GB at 100k nodes)", "nodes": n},
+            "cpu_baseline": {"value": v, "unit": "nodes/s", "cores": threads, "kind": "port",
+                             "sample": f"oracle port of the patched reference forward (P1-P7), {n}-node graph, best of {len(times)} after 1 warm-up"},
+            "e2e": {"value": v, "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--nodes", type=int, default=100000)
+    ap.add_argument("--ref-nodes", type=int, default=2000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from dgdm_histopath_lab_b200 import DGDMModel, Data, _lib, ops, synth
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.load()
+    ops.device_check(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = DGDMModel(**BASE_CFG).eval()
+    model.load_state_dict(synth.seeded_state_dict(model, 0))
+    model = model.to(dev)
+    if world > 1:
+        model.set_distributed(rank, world)
+    host = synth.tile_graph(args.nodes, 768, seed=1234)
+    N, E = host.x.size(0), host.edge_index.size(1)
+    data = host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return model(data, return_embeddings=True)
+
+    for _ in range(args.warmup):
+        out = step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ops.LAUNCHES["kernels"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step_resident()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ops.LAUNCHES["kernels"] - l0
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    value = N * args.steps / (ms / 1e3)
+
+    # ---- end to end through the public API with host buffers
+    e2e = None
+    if not args.no_e2e:
+        hx, hei, hpos = host.x.pin_memory(), host.edge_index.pin_memory(), host.pos.pin_memory()
+        h2d = hx.numel() * 4 + hei.numel() * 8 + hpos.numel() * 4
+
+        def step_e2e():
+            d = Data(x=hx.to(dev, non_blocking=True), edge_index=hei.to(dev, non_blocking=True), pos=hpos.to(dev, non_blocking=True))
+            o = model(d)
+            return o["graph_embedding"].cpu()
+
+        for _ in range(2):
+            g = step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            g = step_e2e()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": N * args.steps / dt, "unit": "nodes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": g.numel() * 4,
+               "ms_per_step": 1e3 * dt / args.steps}
+
+    # ---- per-kernel-class timing pass (CUDA events after every C-ABI call on the launching stream)
+    pk = peaks()
+    ops.profile_begin()
+    step_resident()
+    prof = ops.profile_end()
+    meta = ops.take_profile_meta()
+    att_ms = prof.get("dgdm_spatial_attention", [0, 0.0])[1]
+    spmm_ms = prof.get("dgdm_spmm_gcn", [0, 0.0])[1]
+    gemm_ms = prof.get("dgdm_gemm_f16x2", [0, 0.0])[1]
+    nq = N if world == 1 else -(-N // world)
+    att_flops = 4.0 * nq * N * 128 + 0.0                                      # QK^T + PV, per rank (query rows sharded)
+    att_exp = 8.0 * nq * N
+    spmm_bytes = sum((e + n) * c * 4 + n * c * 4 + (e + n) * 8 + (n + 1) * 4 for (n, e, c) in meta.get("spmm", []))
+    gemm_flops = sum(2.0 * m * k * n_ for (m, k, n_) in meta.get("gemm", []))
+    roof = {"kernel": "spatial_attn_kernel<16,precise>", "bound": "tensor", "achieved": att_flops / (att_ms * 1e-3) / 1e12 if att_ms else None,
+            "peak": pk["tf_sustained"], "unit": "TFLOP/s", "traffic": None, "peak_source": pk["src"],
+            "note": "dominant kernel; exp2(MUFU)-bound, not tensor- or HBM-bound: head_dim 16 gives K=16 / N=16 MMAs",
+            "gexp_per_s": att_exp / (att_ms * 1e-3) / 1e9 if att_ms else None, "ms": att_ms}
+    roof["frac"] = roof["achieved"] / roof["peak"] if roof["achieved"] else None
+    roof_hbm = {"kernel": "spmm_gcn_kernel (all launches)", "bound": "hbm", "achieved": spmm_bytes / (spmm_ms * 1e-3) / 1e9 if spmm_ms else None,
+                "peak": pk["hbm"], "unit": "GB/s", "traffic": None, "ms": spmm_ms, "launches": len(meta.get("spmm", [])),
+                "algorithmic_bytes": spmm_bytes}
+    roof_hbm["frac"] = roof_hbm["achieved"] / roof_hbm["peak"] if roof_hbm["achieved"] else None
+    roof_gemm = {"kernel": "gemm_f16x2_kernel (all launches)", "bound": "tensor", "achieved": 3 * gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None,
+                 "peak": pk["tf_sustained"], "unit": "TFLOP/s (3 MMA passes counted)", "ms": gemm_ms, "launches": len(meta.get("gemm", []))}
+    roof_gemm["frac"] = roof_gemm["achieved"] / roof_gemm["peak"] if roof_gemm["achieved"] else None
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        v, threads, times = oracle_nodes_per_sec(args.ref_nodes, 2)
+        cpu = {"value": v, "unit": "nodes/s", "cores": threads, "kind": "port",
+               "sample": f"oracle port of the patched reference forward on a {args.ref_nodes}-node graph (config 1), best of 2 after 1 warm-up; "
+                         f"the 100k-node workload is infeasible on CPU (dense attention scores = 320 GB)"}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"DGDM-Base forward (eval, inference mode, return_embeddings) on one synthetic {N}-node 768-d tile graph, "
+                                       f"E={E} directed edges, random-init seeded weights", "nodes": N, "edges": E,
+                           "l2_policy": "inputs larger than L2 (x = 307 MB, activations > 200 MB per layer)",
+                           "parallelism": "single GPU" if world == 1 else f"spatial attention sharded by query rows over {world} GPUs "
+                                          f"(NCCL all-gather of outputs), encoder/U-Net replicated",
+                           "attention_precise": ops.attention_precise_default(), "gemm": ops.gemm_mode()},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "roofline_hbm": roof_hbm, "roofline_gemm": roof_gemm,
+                "cpu_baseline": cpu, "per_call_ms": {k: round(v[1], 4) for k, v in prof.items()},
+                "graph_embedding_checksum": float(out["graph_embedding"].double().abs().sum().item())}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -15,7 +15,23 @@ import torch.nn.functional as F
 from . import ops
 from .graph import GraphContext
 
-_SPLIT_CACHE = weakref.WeakKeyDictionary()
+class _IdCache:
+    """Cache keyed on the identity of a Parameter (tensors cannot be dict keys by value); entries die with the parameter."""
+
+    def __init__(self):
+        self._d = {}
+
+    def get(self, obj):
+        return self._d.get(id(obj))
+
+    def put(self, obj, value):
+        i = id(obj)
+        if i not in self._d:
+            weakref.finalize(obj, self._d.pop, i, None)
+        self._d[i] = value
+
+
+_SPLIT_CACHE = _IdCache()
 _CAT_CACHE = {}
 
 
@@ -25,7 +41,7 @@ def split_weight(param):
     hit = _SPLIT_CACHE.get(param)
     if hit is None or hit[0] != key:
         hit = (key, ops.SplitWeight(param.detach()))
-        _SPLIT_CACHE[param] = hit
+        _SPLIT_CACHE.put(param, hit)
     return hit[1]
 
 
@@ -202,7 +218,7 @@ class AdaptiveGraphPooling(nn.Module):
         return px, pei, pea, perm.long()
 
 
-_SCALAR_CACHE = weakref.WeakKeyDictionary()
+_SCALAR_CACHE = _IdCache()
 
 
 def _host_scalar(param):
@@ -210,7 +226,7 @@ def _host_scalar(param):
     hit = _SCALAR_CACHE.get(param)
     if hit is None or hit[0] != key:
         hit = (key, float(param.detach().reshape(-1)[0].item()))
-        _SCALAR_CACHE[param] = hit
+        _SCALAR_CACHE.put(param, hit)
     return hit[1]
 
 
@@ -388,7 +404,7 @@ class SpatialAttention(nn.Module):
         w, bias = att.qkv_weight()
         qkv = ops.linear(xp, w, bias)
         if kv_gather is not None:
-            o = kv_gather(qkv, pos)
+            o = kv_gather(qkv, pos, seg_ptr, num_seg, self.num_heads, self.temperature)
         else:
             o = ops.spatial_attention(qkv, pos, seg_ptr, num_seg, self.num_heads, self.temperature)
         out = ops.linear(o, split_weight(att.out_proj.weight), att.out_proj.bias.detach(), r_pre=x, ln1=_ln(self.norm))
@@ -517,7 +533,6 @@ class DiffusionLayer(nn.Module):
         d0, g1, d4, g5, d8 = (self.denoise_net[i] for i in (0, 1, 4, 5, 8))
         emb = self.get_timestep_embedding(seg_t.to(x2.device))                                  # [S,128] tiny, host-driven
         nseg = emb.size(0)
-        pad = (-nseg) % 1
         t1 = ops.linear(emb.contiguous(), split_weight(te0.weight), te0.bias.detach(), act_post="silu")
         t2 = ops.linear(t1, split_weight(te2.weight), te2.bias.detach())                        # [S, hidden]
         wx, wt = _split_cols(d0.weight, self.node_dim)
@@ -572,7 +587,7 @@ class DiffusionLayer(nn.Module):
         return x
 
 
-_COLSPLIT_CACHE = weakref.WeakKeyDictionary()
+_COLSPLIT_CACHE = _IdCache()
 
 
 def _split_cols(param, k0):
@@ -582,7 +597,7 @@ def _split_cols(param, k0):
     if hit is None or hit[0] != key:
         w = param.detach()
         hit = (key, ops.SplitWeight(w[:, :k0].contiguous()), ops.SplitWeight(w[:, k0:].contiguous()))
-        _COLSPLIT_CACHE[param] = hit
+        _COLSPLIT_CACHE.put(param, hit)
     return hit[1], hit[2]
 
 

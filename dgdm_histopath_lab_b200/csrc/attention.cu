@@ -15,7 +15,8 @@
 
 namespace dgdm {
 
-constexpr int ATT_WARPS = 8;
+constexpr int ATT_WARPS = 8;                 // row groups (16 query rows each) per CTA
+constexpr int ATT_THREADS = 2 * ATT_WARPS * 32; // 16 warps: two head-halves x 8 row groups
 constexpr int ATT_QT = ATT_WARPS * 16;      // 128 query rows per CTA
 constexpr int ATT_KS = 64;                  // keys per smem stage
 constexpr int ATT_DG = 128;                 // columns (heads_in_group * head_dim) handled per CTA
@@ -55,17 +56,20 @@ __device__ __forceinline__ void cp8(uint32_t dst, const void* src, bool valid) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
 }
 
-template <int HD, bool PRECISE>
-__global__ void __launch_bounds__(ATT_WARPS * 32, 1) spatial_attn_kernel(const AttnParams p) {
+template <int HD, bool PRECISE, bool FULL>
+__global__ void __launch_bounds__(ATT_THREADS, 1) spatial_attn_kernel(const AttnParams p) {
   static_assert(HD == 16, "head_dim 16 specialisation");
-  constexpr int G = ATT_DG / HD;                       // heads per CTA (8)
+  constexpr int G = ATT_DG / HD / 2;                   // heads per warp (4): warps 0-7 own heads 0-3, warps 8-15 heads 4-7
   constexpr int NPL = PRECISE ? 2 : 1;                 // fp16 planes per operand
+  constexpr int KB = PRECISE ? 16 : 32;                // keys per inner block (register budget: 128 regs/thread)
+  constexpr int NT = KB / 8;                           // 8-key n-tiles per inner block
   constexpr int PLANE_B = ATT_KS * ATT_ROWB;           // bytes per K or V plane per stage
   constexpr int STAGE_B = 2 * NPL * PLANE_B + ATT_KS * 8;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int rw = warp & (ATT_WARPS - 1), hh = warp / ATT_WARPS;     // row group, head half
   // ---- locate this CTA's (segment, query tile)
   int seg = -1, row0 = 0;
   {
@@ -85,20 +89,21 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 1) spatial_attn_kernel(const A
   per = (per + ATT_KS - 1) / ATT_KS * ATT_KS;
   const int ks = kbeg + split * per;
   const int ke = min(kend, ks + per);
-  const int hg = blockIdx.z;                           // head group
-  const int col0 = hg * ATT_DG;                        // first column of this head group
-  const int nheads = min(G, p.heads - hg * G);
+  const int hg = blockIdx.z;                           // head group of 8 heads (128 columns)
+  const int col0 = hg * ATT_DG;                        // first column staged in smem
+  const int head0 = hg * (2 * G) + hh * G;             // first head of this warp
+  const int nheads = FULL ? G : max(0, min(G, p.heads - head0));
 
-  const int r_lo = row0 + warp * 16 + g, r_hi = r_lo + 8;
-  const bool warp_active = (row0 + warp * 16) < qend;
+  const int r_lo = row0 + rw * 16 + g, r_hi = r_lo + 8;
+  const bool warp_active = (row0 + rw * 16) < qend && nheads > 0;
   const int rl = min(r_lo, qend - 1), rh = min(r_hi, qend - 1);
 
   // ---- Q fragments (A operand, 16x16 per head), query positions
   uint32_t qh[G][4], ql[PRECISE ? G : 1][4];
 #pragma unroll
   for (int h = 0; h < G; ++h) {
-    const int c = col0 + h * HD + 2 * t;
-    const bool hv = h < nheads;
+    const int c = (head0 + h) * HD + 2 * t;
+    const bool hv = FULL || h < nheads;
     qh[h][0] = hv ? *reinterpret_cast<const uint32_t*>(p.Qh + (size_t)rl * p.D + c) : 0u;
     qh[h][1] = hv ? *reinterpret_cast<const uint32_t*>(p.Qh + (size_t)rh * p.D + c) : 0u;
     qh[h][2] = hv ? *reinterpret_cast<const uint32_t*>(p.Qh + (size_t)rl * p.D + c + 8) : 0u;
@@ -127,7 +132,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 1) spatial_attn_kernel(const A
   // ---- K/V stage loader (all threads)
   auto load_stage = [&](int stage, int key0) {
     const uint32_t st = sbase + stage * STAGE_B;
-    for (int i = tid; i < ATT_KS * 16; i += ATT_WARPS * 32) {     // 16-byte chunks: 64 rows x 16 per plane
+    for (int i = tid; i < ATT_KS * 16; i += ATT_THREADS) {        // 16-byte chunks: 64 rows x 16 per plane
       const int r = i >> 4, c = i & 15;
       const int key = key0 + r;
       const bool v = key < ke && (col0 + c * 8) < p.D;      // zero-fill padded keys and columns beyond D
@@ -159,12 +164,12 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 1) spatial_attn_kernel(const A
       const float4* kp4 = reinterpret_cast<const float4*>(smem + (si & 1) * STAGE_B + 2 * NPL * PLANE_B);
       const int key0 = ks + si * ATT_KS;
 #pragma unroll 1
-      for (int kb = 0; kb < ATT_KS; kb += 32) {
+      for (int kb = 0; kb < ATT_KS; kb += KB) {
         if (key0 + kb >= ke) break;
-        // ---- bias tile: 4 n-tiles x (2 rows x 2 cols); -|p_i - p_j| (positions pre-scaled by log2e/T), -inf for padded keys
-        float bias[4][4];
+        // ---- bias tile: NT n-tiles x (2 rows x 2 cols); -|p_i - p_j| (positions pre-scaled by log2e/T), -inf for padded keys
+        float bias[NT][4];
 #pragma unroll
-        for (int n = 0; n < 4; ++n) {
+        for (int n = 0; n < NT; ++n) {
           const int kk = kb + n * 8 + 2 * t;                // keys kk, kk+1 of this stage
           float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
           if (p.use_bias) {
@@ -180,12 +185,13 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 1) spatial_attn_kernel(const A
         }
 #pragma unroll
         for (int h = 0; h < G; ++h) {
-          if (h >= nheads) break;
-          // ---- S = Q K^T + bias : 4 n-tiles of 8 keys
-          float s[4][4];
-          const uint32_t kaddr = sK + (kb + (lane >> 4) * 8 + (lane & 7)) * ATT_ROWB + h * (HD * 2) + ((lane >> 3) & 1) * 16;
+          if (!FULL && h >= nheads) break;
+          const int hc = (hh * G + h) * (HD * 2);           // byte offset of this head inside a staged row
+          // ---- S = Q K^T + bias : NT n-tiles of 8 keys
+          float s[NT][4];
+          const uint32_t kaddr = sK + (kb + (lane >> 4) * 8 + (lane & 7)) * ATT_ROWB + hc + ((lane >> 3) & 1) * 16;
 #pragma unroll
-          for (int n2 = 0; n2 < 2; ++n2) {                  // each ldmatrix.x4 covers 16 keys (2 n-tiles)
+          for (int n2 = 0; n2 < NT / 2; ++n2) {             // each ldmatrix.x4 covers 16 keys (2 n-tiles)
             uint32_t kf[4];
             ldsm4(kf, kaddr + n2 * 16 * ATT_ROWB);
             mma16816(s[2 * n2], qh[h], kf[0], kf[1], bias[2 * n2]);
@@ -200,10 +206,10 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 1) spatial_attn_kernel(const A
             }
           }
           // ---- lazy-max softmax
-          float pr[4][4];
+          float pr[NT][4];
           float sum_lo = 0.f, sum_hi = 0.f;
 #pragma unroll
-          for (int n = 0; n < 4; ++n) {
+          for (int n = 0; n < NT; ++n) {
             pr[n][0] = ex2(s[n][0] - m_lo[h]); pr[n][1] = ex2(s[n][1] - m_lo[h]);
             pr[n][2] = ex2(s[n][2] - m_hi[h]); pr[n][3] = ex2(s[n][3] - m_hi[h]);
             sum_lo += pr[n][0] + pr[n][1]; sum_hi += pr[n][2] + pr[n][3];
@@ -212,7 +218,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 1) spatial_attn_kernel(const A
           if (__any_sync(0xffffffffu, bad)) {
             float mx_lo = m_lo[h], mx_hi = m_hi[h];
 #pragma unroll
-            for (int n = 0; n < 4; ++n) {
+            for (int n = 0; n < NT; ++n) {
               mx_lo = fmaxf(mx_lo, fmaxf(s[n][0], s[n][1])); mx_hi = fmaxf(mx_hi, fmaxf(s[n][2], s[n][3]));
             }
             mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1)); mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
@@ -226,17 +232,17 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 1) spatial_attn_kernel(const A
             for (int n = 0; n < 2; ++n) { o[h][n][0] *= sc_lo; o[h][n][1] *= sc_lo; o[h][n][2] *= sc_hi; o[h][n][3] *= sc_hi; }
             sum_lo = 0.f; sum_hi = 0.f;
 #pragma unroll
-            for (int n = 0; n < 4; ++n) {
+            for (int n = 0; n < NT; ++n) {
               pr[n][0] = ex2(s[n][0] - ml); pr[n][1] = ex2(s[n][1] - ml);
               pr[n][2] = ex2(s[n][2] - mh); pr[n][3] = ex2(s[n][3] - mh);
               sum_lo += pr[n][0] + pr[n][1]; sum_hi += pr[n][2] + pr[n][3];
             }
           }
           l_lo[h] += sum_lo; l_hi[h] += sum_hi;
-          // ---- O += P V : two k16 steps (16 keys each) x two n-tiles (8 dims each)
-          const uint32_t vaddr = sV + (kb + ((lane >> 3) & 1) * 8 + (lane & 7)) * ATT_ROWB + h * (HD * 2) + (lane >> 4) * 16;
+          // ---- O += P V : KB/16 k16 steps (16 keys each) x two n-tiles (8 dims each)
+          const uint32_t vaddr = sV + (kb + ((lane >> 3) & 1) * 8 + (lane & 7)) * ATT_ROWB + hc + (lane >> 4) * 16;
 #pragma unroll
-          for (int k2 = 0; k2 < 2; ++k2) {
+          for (int k2 = 0; k2 < NT / 2; ++k2) {
             uint32_t pa[4], vf[4];
             pa[0] = pack_h2(pr[2 * k2][0], pr[2 * k2][1]);     pa[1] = pack_h2(pr[2 * k2][2], pr[2 * k2][3]);
             pa[2] = pack_h2(pr[2 * k2 + 1][0], pr[2 * k2 + 1][1]); pa[3] = pack_h2(pr[2 * k2 + 1][2], pr[2 * k2 + 1][3]);
@@ -269,20 +275,20 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 1) spatial_attn_kernel(const A
   if (warp_active) {
 #pragma unroll
     for (int h = 0; h < G; ++h) {
-      if (h >= nheads) break;
+      if (!FULL && h >= nheads) break;
       float ll = l_lo[h], lh = l_hi[h];
       ll += __shfl_xor_sync(0xffffffffu, ll, 1); ll += __shfl_xor_sync(0xffffffffu, ll, 2);
       lh += __shfl_xor_sync(0xffffffffu, lh, 1); lh += __shfl_xor_sync(0xffffffffu, lh, 2);
-      const int head = hg * G + h;
+      const int head = head0 + h;
       const size_t pbase = (size_t)split * p.Nq;
       if (r_lo < qend) {
-        float* op = p.Opart + (pbase + r_lo) * p.D + col0 + h * HD + 2 * t;
+        float* op = p.Opart + (pbase + r_lo) * p.D + head * HD + 2 * t;
         *reinterpret_cast<float2*>(op) = make_float2(o[h][0][0], o[h][0][1]);
         *reinterpret_cast<float2*>(op + 8) = make_float2(o[h][1][0], o[h][1][1]);
         if (t == 0) { p.Mpart[(pbase + r_lo) * p.heads + head] = m_lo[h]; p.Lpart[(pbase + r_lo) * p.heads + head] = ll; }
       }
       if (r_hi < qend) {
-        float* op = p.Opart + (pbase + r_hi) * p.D + col0 + h * HD + 2 * t;
+        float* op = p.Opart + (pbase + r_hi) * p.D + head * HD + 2 * t;
         *reinterpret_cast<float2*>(op) = make_float2(o[h][0][2], o[h][0][3]);
         *reinterpret_cast<float2*>(op + 8) = make_float2(o[h][1][2], o[h][1][3]);
         if (t == 0) { p.Mpart[(pbase + r_hi) * p.heads + head] = m_hi[h]; p.Lpart[(pbase + r_hi) * p.heads + head] = lh; }
@@ -523,17 +529,21 @@ extern "C" int dgdm_spatial_attention(const float* q_qkv, int ld_q, const float*
   const int tiles = (Nq + ATT_QT - 1) / ATT_QT + num_seg;
   const int hgroups = (D + ATT_DG - 1) / ATT_DG;
   dim3 grid(tiles, ns, hgroups);
-  if (precise) {
-    constexpr int smem = 2 * (4 * ATT_KS * ATT_ROWB + ATT_KS * 8);
-    static bool set = false;
-    if (!set) { if (cudaFuncSetAttribute(spatial_attn_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return DGDM_ERR_LAUNCH; set = true; }
-    spatial_attn_kernel<16, true><<<grid, ATT_WARPS * 32, smem, s>>>(p);
-  } else {
-    constexpr int smem = 2 * (2 * ATT_KS * ATT_ROWB + ATT_KS * 8);
-    static bool set = false;
-    if (!set) { if (cudaFuncSetAttribute(spatial_attn_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return DGDM_ERR_LAUNCH; set = true; }
-    spatial_attn_kernel<16, false><<<grid, ATT_WARPS * 32, smem, s>>>(p);
-  }
+  const bool full = (heads % 8) == 0;
+#define ATT_LAUNCH(PREC, FULLV)                                                                                          \
+  do {                                                                                                                   \
+    constexpr int smem = 2 * ((PREC ? 4 : 2) * ATT_KS * ATT_ROWB + ATT_KS * 8);                                          \
+    static bool set = false;                                                                                             \
+    if (!set) {                                                                                                          \
+      if (cudaFuncSetAttribute(spatial_attn_kernel<16, PREC, FULLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)  \
+          != cudaSuccess) return DGDM_ERR_LAUNCH;                                                                        \
+      set = true;                                                                                                        \
+    }                                                                                                                    \
+    spatial_attn_kernel<16, PREC, FULLV><<<grid, ATT_THREADS, smem, s>>>(p);                                             \
+  } while (0)
+  if (precise) { if (full) ATT_LAUNCH(true, true); else ATT_LAUNCH(true, false); }
+  else         { if (full) ATT_LAUNCH(false, true); else ATT_LAUNCH(false, false); }
+#undef ATT_LAUNCH
   attn_combine_kernel<<<agrid((size_t)Nq * (D / 4)), 256, 0, s>>>(Opart, Mpart, Lpart, ns, Nq, D, heads, out, ldo);
   DGDM_CHECK_LAUNCH();
   return DGDM_OK;

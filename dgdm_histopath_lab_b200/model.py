@@ -184,6 +184,30 @@ class DGDMModel(nn.Module):
         if regression_targets > 0:
             self.regression_head = RegressionHead(hidden_dims[-1], regression_targets, [hidden_dims[-1] // 2], dropout, activation)
         self.apply(self._init_weights)
+        self._dist = None
+
+    # -------------------------------------------------------------------------------------- multi-GPU
+    def set_distributed(self, rank, world, group=None):
+        """One process per GPU (torch.distributed, NCCL). The O(N^2) spatial attention — ~90% of the forward at 100k nodes —
+        is sharded by query rows (each rank keeps the full K/V, which it computes itself: 2 x N x 128 fp16 = 51 MB at 100k),
+        its [N/P, D] outputs are all-gathered over NVLink; the O(N) encoder / U-Net are replicated."""
+        self._dist = (int(rank), int(world), group) if world and world > 1 else None
+
+    def _dist_attention(self, qkv, pos, seg_ptr, num_seg, heads, temperature):
+        import torch.distributed as dist
+        rank, world, group = self._dist
+        n, d3 = qkv.shape
+        rows = -(-n // world)
+        r0, r1 = min(n, rank * rows), min(n, (rank + 1) * rows)
+        out = torch.zeros(rows, d3 // 3, dtype=torch.float32, device=qkv.device)
+        if r1 > r0:
+            qseg = (torch.clamp(seg_ptr, r0, r1) - r0).to(torch.int32)
+            o = ops.spatial_attention(qkv[r0:r1], pos[r0:r1].contiguous(), qseg, num_seg, heads, temperature,
+                                      kv_qkv=qkv, kv_pos=pos, kseg_ptr=seg_ptr)
+            out[:r1 - r0] = o
+        full = torch.empty(world * rows, d3 // 3, dtype=torch.float32, device=qkv.device)
+        dist.all_gather_into_tensor(full, out, group=group)
+        return full[:n]
 
     # -------------------------------------------------------------------------------------- construction
     def _validate_configuration(self, node_features, hidden_dims, num_diffusion_steps, attention_heads, dropout, graph_layers,
@@ -308,7 +332,8 @@ class DGDMModel(nn.Module):
         h = self.graph_encoder(h, ctx=ctx, edge_attr=edge_attr)["embeddings"]
         outputs, attn = {}, None
         if self.spatial_attention is not None and pos is not None:
-            h, attn = self.spatial_attention.forward_nodes(h, pos, ctx.seg_ptr, ctx.num_graphs, ctx.seg_host, return_attention)
+            h, attn = self.spatial_attention.forward_nodes(h, pos, ctx.seg_ptr, ctx.num_graphs, ctx.seg_host, return_attention,
+                                                           kv_gather=self._dist_attention if self._dist is not None else None)
             if attn is not None and batch is None:
                 attn = attn[0]
         if self.hierarchical_processor is not None:

@@ -38,9 +38,20 @@ def _check(rc, name):
         _PROFILE.append((name, ev))
 
 
+_PROFILE_META = {}
+
+
+def take_profile_meta():
+    """Shapes recorded during the last profile pass: {'spmm': [(rows, edges, C)], 'gemm': [(M, K, N)]}."""
+    global _PROFILE_META
+    m, _PROFILE_META = _PROFILE_META, {}
+    return m
+
+
 def profile_begin():
     """Start recording one CUDA event after every C-ABI call on the current stream (durations = gaps between events)."""
-    global _PROFILE
+    global _PROFILE, _PROFILE_META
+    _PROFILE_META = {}
     _PROFILE = []
     ev = torch.cuda.Event(enable_timing=True)
     ev.record()
@@ -142,6 +153,8 @@ def linear(a, w, bias=None, *, r_pre=None, act_pre=None, ln1=None, ln2=None, act
     if row_bias is not None:
         keep = row_bias
         p.row_bias_index, p.row_bias, p.ld_row_bias = _p(row_bias[0]), _p(row_bias[1]), row_bias[1].stride(0)
+    if _PROFILE is not None:
+        _PROFILE_META.setdefault("gemm", []).append((M, K, N))
     if M > 0:
         if mode == "simt":
             _check(lib.dgdm_gemm_simt(C.byref(p), _p(w.w32), _stream()), "dgdm_gemm_simt")
@@ -203,6 +216,8 @@ def spmm_gcn(csr, h, *, n_rows=None, addend=None, bias=None, act=None, out=None)
     assert h.stride(1) == 1 and h.size(0) >= n_rows
     if out is None:
         out = torch.empty(n_rows, Cw, dtype=torch.float32, device=h.device)
+    if _PROFILE is not None:      # profiling pass only: the edge count of pooled levels lives on the device
+        _PROFILE_META.setdefault("spmm", []).append((n_rows, int(csr.rowptr[min(csr.N, n_rows)].item()), Cw))
     _check(lib.dgdm_spmm_gcn(_p(csr.rowptr), _p(csr.col), _p(csr.norm), _p(csr.dinv), min(csr.N, n_rows), n_rows,
                              _p(_f32c(h)), h.stride(0), Cw, _p(addend), addend.stride(0) if addend is not None else 0,
                              _p(bias), ACT[act], _p(out), out.stride(0), _stream()), "dgdm_spmm_gcn")

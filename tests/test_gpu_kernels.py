@@ -110,7 +110,7 @@ def _ref_linear(a, w, bias, r_pre, act_pre, ln1, ln2, act_post, r_post):
 def test_linear_plain(mode, M, K, N):
     a = torch.randn(M, K, generator=_gen(M + K)); w = torch.randn(N, K, generator=_gen(N)) / K ** 0.5
     out = ops.linear(a.to(DEV), ops.SplitWeight(w.to(DEV)), mode=mode)
-    assert rel_err(out, a.double() @ w.double().t())[0] < 3e-6
+    assert rel_err(out, a.double() @ w.double().t())[0] < 6e-6
 
 
 @pytest.mark.parametrize("N", [64, 128, 512])

@@ -42,6 +42,49 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   }
 }
 
+// Activation over a register chunk with the switch hoisted OUT of the element loop: a per-element runtime switch
+// compiles to an indirect branch (BRX) per element, which dominated the GEMM epilogue (60 us for a single CTA).
+template <int ACT>
+__device__ __forceinline__ float act_const(float x) {
+  if constexpr (ACT == DGDM_ACT_GELU) return gelu_erf(x);
+  else if constexpr (ACT == DGDM_ACT_RELU) return fmaxf(x, 0.0f);
+  else if constexpr (ACT == DGDM_ACT_SILU) return silu(x);
+  else if constexpr (ACT == DGDM_ACT_TANH) return tanhf(x);
+  else if constexpr (ACT == DGDM_ACT_ELU) return x > 0.0f ? x : expm1f(x);
+  else return x;
+}
+template <int N>
+__device__ __forceinline__ void apply_act_chunk(float* v, int act) {
+  switch (act) {
+    case DGDM_ACT_GELU:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = act_const<DGDM_ACT_GELU>(v[j]);
+      break;
+    case DGDM_ACT_RELU:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = act_const<DGDM_ACT_RELU>(v[j]);
+      break;
+    case DGDM_ACT_SILU:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = act_const<DGDM_ACT_SILU>(v[j]);
+      break;
+    case DGDM_ACT_TANH:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = act_const<DGDM_ACT_TANH>(v[j]);
+      break;
+    case DGDM_ACT_ELU:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = act_const<DGDM_ACT_ELU>(v[j]);
+      break;
+    default: break;
+  }
+}
+__device__ __forceinline__ void apply_act4(float4& a, int act) {
+  float v[4] = {a.x, a.y, a.z, a.w};
+  apply_act_chunk<4>(v, act);
+  a = make_float4(v[0], v[1], v[2], v[3]);
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // order-preserving float <-> uint mapping (for atomic min/max and radix select)

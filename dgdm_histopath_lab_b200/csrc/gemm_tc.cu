@@ -264,8 +264,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16x2_kernel(const dgdm_
     float sum = 0.f, dot = 0.f;
 
     auto finish = [&](int c0) {   // v holds the post-LN values of columns [c0, c0+32)
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act_post);
+      apply_act_chunk<32>(v, p.act_post);
       if (p.r_post != nullptr) {
         warp_load_tile(st, t, p.r_post, p.ld_r_post, row0, c0, p.M, p.N, lane);
 #pragma unroll
@@ -290,11 +289,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16x2_kernel(const dgdm_
           if (p.bias != nullptr) x += __ldg(p.bias + c);
           if (p.row_bias != nullptr) x += __ldg(p.row_bias + (size_t)rbi * p.ld_row_bias + c);
           if (p.r_pre != nullptr) x += t[j];
-          x = apply_act(x, p.act_pre);
-          sum += x;
         } else x = 0.f;
         v[j] = x;
       }
+      if (p.act_pre != DGDM_ACT_NONE) {
+        apply_act_chunk<32>(v, p.act_pre);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (c0 + j >= p.N) v[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sum += v[j];
       if (writeback) tmem_st32(t_row + (uint32_t)c0, v);
       else finish(c0);
     }

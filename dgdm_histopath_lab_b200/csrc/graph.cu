@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) spmm_gcn_kernel(const int* __restrict__ r
       a.x = fmaf(selfw, hs.x, a.x); a.y = fmaf(selfw, hs.y, a.y); a.z = fmaf(selfw, hs.z, a.z); a.w = fmaf(selfw, hs.w, a.w);
       if (addend) { const float4 t = ldg4(addend + (size_t)row * ld_add + idx); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
       if (bias) { const float4 t = ldg4(bias + idx); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
-      a.x = apply_act(a.x, act); a.y = apply_act(a.y, act); a.z = apply_act(a.z, act); a.w = apply_act(a.w, act);
+      apply_act4(a, act);
       *reinterpret_cast<float4*>(out + (size_t)row * ldo + idx) = a;
     }
   }
@@ -249,7 +249,8 @@ __global__ void __launch_bounds__(256) pool_gather_kernel(const float* __restric
     const int src = perm[r];
     const float sc = s[src];
     float4 v = ldg4(X + (size_t)src * ldx + c);
-    v.x = apply_act(v.x * sc, act); v.y = apply_act(v.y * sc, act); v.z = apply_act(v.z * sc, act); v.w = apply_act(v.w * sc, act);
+    v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+    apply_act4(v, act);
     *reinterpret_cast<float4*>(out + (size_t)r * ldo + c) = v;
   }
 }

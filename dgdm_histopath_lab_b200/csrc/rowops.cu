@@ -64,8 +64,7 @@ __global__ void __launch_bounds__(256) rowwise_epilogue_kernel(const float* __re
       if (p.bias) { float4 b = ldg4(p.bias + c); x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w; }
       if (p.row_bias) { float4 b = ldg4(p.row_bias + (size_t)rbi * p.ld_row_bias + c); x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w; }
       if (p.r_pre) { float4 b = ldg4(p.r_pre + (size_t)m * p.ld_r_pre + c); x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w; }
-      x.x = apply_act(x.x, p.act_pre); x.y = apply_act(x.y, p.act_pre);
-      x.z = apply_act(x.z, p.act_pre); x.w = apply_act(x.w, p.act_pre);
+      apply_act4(x, p.act_pre);
       sum += (x.x + x.y) + (x.z + x.w);
     }
     v[j] = x;
@@ -103,8 +102,7 @@ __global__ void __launch_bounds__(256) rowwise_epilogue_kernel(const float* __re
     const int c = (j * 32 + lane) * 4;
     if (c < N) {
       float4 x = v[j];
-      x.x = apply_act(x.x, p.act_post); x.y = apply_act(x.y, p.act_post);
-      x.z = apply_act(x.z, p.act_post); x.w = apply_act(x.w, p.act_post);
+      apply_act4(x, p.act_post);
       if (p.r_post) { float4 b = ldg4(p.r_post + (size_t)m * p.ld_r_post + c); x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w; }
       if (p.dot_w) { float4 w = ldg4(p.dot_w + c); dot += x.x * w.x + x.y * w.y + x.z * w.z + x.w * w.w; }
       if (p.C) *reinterpret_cast<float4*>(p.C + (size_t)m * p.ldc + c) = x;
@@ -213,7 +211,7 @@ __global__ void __launch_bounds__(256) unpool_add_act_kernel(const float* __rest
     float4 s = ldg4(skip + (size_t)row * lds + c);
     const int j = node_map[row];
     if (j >= 0) { float4 u = ldg4(x + (size_t)j * ldx + c); s.x += u.x; s.y += u.y; s.z += u.z; s.w += u.w; }
-    s.x = apply_act(s.x, act); s.y = apply_act(s.y, act); s.z = apply_act(s.z, act); s.w = apply_act(s.w, act);
+    apply_act4(s, act);
     *reinterpret_cast<float4*>(out + (size_t)row * ldo + c) = s;
   }
 }

@@ -6,7 +6,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["gemm_tc.cu", "rowops.cu", "graph.cu", "attention.cu", "builder.cu"]
+SOURCES = ["gemm_tc.cu", "rowops.cu", "graph.cu", "attention.cu", "attention_tc.cu", "builder.cu"]
 LIB_PATH = os.path.join(HERE, "libdgdm_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
@@ -23,7 +23,7 @@ def needs_build():
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh"),
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc05.cuh"),
                                                        os.path.join(HERE, "..", "include", "dgdm_b200.h")]
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 

@@ -480,18 +480,32 @@ static int choose_nsplit(int Nq, int Nkv, int num_seg) {
   return s;
 }
 
+void attn_launch_combine(const float* Opart, const float* Mpart, const float* Lpart, int nsplit, int Nq, int D, int heads,
+                         float* out, int ldo, cudaStream_t s) {
+  attn_combine_kernel<<<agrid((size_t)Nq * (D / 4)), 256, 0, s>>>(Opart, Mpart, Lpart, nsplit, Nq, D, heads, out, ldo);
+}
+// attention_tc.cu: tcgen05 / TMEM path (D = 128, 8 heads)
+size_t attn_tc_work_bytes(int Nq, int Nkv, int D, int heads, int num_seg);
+int attn_tc_launch(const float* q_qkv, int ld_q, const float* q_pos, const int* qseg_ptr, int Nq,
+                   const float* kv_qkv, int ld_kv, const float* kv_pos, const int* kseg_ptr, int Nkv,
+                   int num_seg, float temperature, float* out, int ldo, void* work, size_t work_bytes, cudaStream_t s);
+
 }  // namespace dgdm
 using namespace dgdm;
 
 extern "C" size_t dgdm_spatial_attention_work_bytes(int Nq, int Nkv, int D, int heads, int num_seg) {
   const int ns = choose_nsplit(Nq, Nkv, num_seg);
   size_t b = 0;
+  if (D == 128 && heads == 8) b = attn_tc_work_bytes(Nq, Nkv, D, heads, num_seg);
+  const size_t b_tc = b;
+  b = 0;
   b += 2 * align256((size_t)Nq * D * 2);            // Qh, Ql
   b += 4 * align256((size_t)Nkv * D * 2);           // Kh, Kl, Vh, Vl
   b += align256((size_t)Nq * 8) + align256((size_t)Nkv * 8);
   b += align256((size_t)ns * Nq * D * 4);
   b += 2 * align256((size_t)ns * Nq * heads * 4);
-  return b + 256;
+  b += 256;
+  return b > b_tc ? b : b_tc;
 }
 
 extern "C" int dgdm_spatial_attention(const float* q_qkv, int ld_q, const float* q_pos, const int* qseg_ptr, int Nq,
@@ -505,6 +519,9 @@ extern "C" int dgdm_spatial_attention(const float* q_qkv, int ld_q, const float*
   if (Nkv <= 0 || num_seg <= 0 || !(temperature > 0.f)) return DGDM_ERR_INVALID;
   if (work_bytes < dgdm_spatial_attention_work_bytes(Nq, Nkv, D, heads, num_seg)) return DGDM_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
+  if (precise == 1 && D == 128 && heads == 8)       // product path for DGDM-Base: tcgen05 / TMEM kernel (attention_tc.cu)
+    return attn_tc_launch(q_qkv, ld_q, q_pos, qseg_ptr, Nq, kv_qkv, ld_kv, kv_pos, kseg_ptr, Nkv, num_seg, temperature, out, ldo,
+                          work, work_bytes, s);
   const int ns = choose_nsplit(Nq, Nkv, num_seg);
   uint8_t* w = (uint8_t*)(((uintptr_t)work + 255) & ~(uintptr_t)255);
   auto take = [&](size_t bytes) { uint8_t* r = w; w += align256(bytes); return r; };

@@ -1,0 +1,484 @@
+// Spatial attention core on tcgen05 / TMEM (head_dim 16, 8 heads, D = 128 — DGDM-Base; core/attention.py:135-157,261-283):
+//   out_i = softmax_j( q_i.k_j / sqrt(hd) - |p_i - p_j| / T ) v_j      per head, keys restricted to the query's graph.
+//
+// The N x N scores are never formed in memory. Work unit = (128 query rows) x (64-key block) x (one head):
+//   S  = Q_h K_h^T        tcgen05.mma kind::f16, M=128 N=64 K=16, A = Q (fp16 hi/lo planes resident in TMEM), B = K tile (smem)
+//   P  = exp2(S - |dp| - m)  by the softmax warps: tcgen05.ld S -> registers -> packed fp32x2 math + MUFU.EX2 -> fp16 hi/lo planes
+//                            written back IN PLACE over S (tcgen05.st), interleaved per 16-key K-step [hi(8 cols) | lo(8 cols)]
+//   O_h += P V_h          tcgen05.mma M=128 N=16 K=16 x 4 K-steps, A = P (TMEM), B = V_h^T tile (smem), accumulator in TMEM
+// All products use the 3-term split (hi*hi + lo*hi + hi*lo) -> fp32-class results (same arithmetic as the mma.sync kernel).
+//
+// CTA = 352 threads: warps 0-3 softmax group 0 (heads 0-3), warps 4-7 softmax group 1 (heads 4-7) — thread = query row, so the
+// distance bias of a (row, key block) is computed once into registers and reused by the group's 4 heads; warps 8/9 issue the MMAs
+// for group 0/1 (one elected thread each); warp 10 streams pre-swizzled K / V^T / position block images global -> smem with
+// cp.async.bulk (TMA engine) through a 3-stage mbarrier ring. TMEM (512 columns): 4 S/P slots x 64 | O 8 x 16 | Q hi 8 x 8 | Q lo 8 x 8.
+// Softmax uses a lazily updated row reference max: a Cauchy-Schwarz bound |q_i| max_j |k_j| per key block decides whether the
+// explicit row-max pass (and an O/l rescale through tcgen05.ld/st) is needed at all; the common path is add, add, exp2, add, split.
+// Roofline: MUFU-bound (one exp2 per score + one sqrt per (row,key) per head group = 1.25 MUFU/score at 16 lanes/clk/SM).
+#include "tc05.cuh"
+
+namespace dgdm {
+
+constexpr int TC_BN = 64;                      // keys per block
+constexpr int TC_QT = 128;                     // query rows per CTA
+constexpr int TC_IMG = 66560;                  // bytes per key-block image (65 KB, keeps every stage 1024-aligned)
+constexpr int TC_OFF_V = 32768;                // K: [plane 2][half 2][64 keys x 128 B]; V^T: [plane 2][head 8][16 dims x 128 B]
+constexpr int TC_OFF_POS = 65536;              // kx[64], ky[64] (pre-scaled by log2e/T; +inf marks padded keys)
+constexpr int TC_OFF_KMAX = 65536 + 512;       // max_j |k_j,h| per head (8 floats)
+constexpr int TC_IMG_USED = 65536 + 512 + 32;  // bytes actually copied per block
+constexpr int TC_STAGES = 3;
+constexpr int TC_THREADS = 352;
+constexpr int TC_SMEM = TC_STAGES * TC_IMG + 1024 + 256;
+constexpr float TC_TAU = 8.0f;                 // lazy-max slack (log2 units): p <= 2^8 stays exact in the fp16 hi/lo split
+
+// TMEM column map
+__device__ __forceinline__ constexpr uint32_t tc_slot(int g, int s) { return (uint32_t)((2 * g + s) * 64); }
+__device__ __forceinline__ constexpr uint32_t tc_ocol(int h) { return (uint32_t)(256 + 16 * h); }
+__device__ __forceinline__ constexpr uint32_t tc_qhi(int h) { return (uint32_t)(384 + 8 * h); }
+__device__ __forceinline__ constexpr uint32_t tc_qlo(int h) { return (uint32_t)(448 + 8 * h); }
+
+struct AttnTcParams {
+  const float* q_qkv; int ld_q; const float* q_pos;
+  const int* qseg; const int* kseg; int num_seg; int Nq; int nsplit;
+  const uint8_t* img; const int* blk_ptr;
+  float qscale, pscale;
+  float* Opart; float* Mpart; float* Lpart;
+};
+
+// ---------------------------------------------------------------------------------------------- packed fp32x2 helpers
+__device__ __forceinline__ unsigned long long pk2(float a, float b) {
+  return (unsigned long long)__float_as_uint(a) | ((unsigned long long)__float_as_uint(b) << 32);
+}
+__device__ __forceinline__ float lo32(unsigned long long v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float hi32(unsigned long long v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+  unsigned long long d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ float tc_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float tc_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ uint32_t tc_pack_h2(float a, float b) {       // a -> low half, b -> high half
+  uint32_t r; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a)); return r;
+}
+__device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint32_t& lo) {   // round-to-nearest hi, residual lo
+  const __half2 h = __floats2half2_rn(a, b);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float2 hf = __half22float2(h);
+  lo = tc_pack_h2(a - hf.x, b - hf.y);
+}
+
+// ---------------------------------------------------------------------------------------------- block-image builder
+__global__ void attn_tc_blkptr_kernel(const int* __restrict__ kseg, int num_seg, int* __restrict__ blk_ptr) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int acc = 0;
+    blk_ptr[0] = 0;
+    for (int g = 0; g < num_seg; ++g) { acc += (kseg[g + 1] - kseg[g] + TC_BN - 1) / TC_BN; blk_ptr[g + 1] = acc; }
+  }
+}
+
+// One CTA per 64-key block: fp32 k|v rows -> fp16 hi/lo planes in the exact shared-memory image the MMA descriptors expect
+// (K-major SWIZZLE_128B tiles), V transposed per head, plus scaled key positions and the per-head max key norm.
+__global__ void __launch_bounds__(256) attn_tc_prep_kernel(const float* __restrict__ kv, int ld, const float* __restrict__ pos,
+                                                           const int* __restrict__ kseg, const int* __restrict__ blk_ptr, int num_seg,
+                                                           float pscale, uint8_t* __restrict__ img) {
+  __shared__ float vt[TC_BN][129];
+  __shared__ float ksq[TC_BN][8];
+  const int gb = blockIdx.x;
+  if (gb >= blk_ptr[num_seg]) return;
+  int lo = 0, hi = num_seg - 1;
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (blk_ptr[mid] <= gb) lo = mid; else hi = mid - 1; }
+  const int key0 = kseg[lo] + (gb - blk_ptr[lo]) * TC_BN;
+  const int nvalid = min(TC_BN, kseg[lo + 1] - key0);
+  uint8_t* out = img + (size_t)gb * TC_IMG;
+  const int tid = threadIdx.x;
+  constexpr int D = 128;
+  // ---- K planes (and squared head norms)
+  for (int idx = tid; idx < TC_BN * 16; idx += 256) {
+    const int r = idx >> 4, c16 = idx & 15;
+    float v[8];
+    if (r < nvalid) {
+      const float4 a = ldg4(kv + (size_t)(key0 + r) * ld + D + c16 * 8), b = ldg4(kv + (size_t)(key0 + r) * ld + D + c16 * 8 + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    }
+    uint32_t h[4], l[4];
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { split_pack(v[2 * i], v[2 * i + 1], h[i], l[i]); sq += v[2 * i] * v[2 * i] + v[2 * i + 1] * v[2 * i + 1]; }
+    const uint32_t off = (uint32_t)((c16 >> 3) * 8192) + tc::sw128_off(r, c16 & 7);
+    *reinterpret_cast<uint4*>(out + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(out + 16384 + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    // head = c16 / 2; the two 8-dim chunks of a head are handled by neighbouring lanes
+    const float other = __shfl_xor_sync(0xffffffffu, sq, 1);
+    if ((c16 & 1) == 0) ksq[r][c16 >> 1] = sq + other;
+  }
+  // ---- V tile -> smem (coalesced), zero rows for padded keys
+  for (int idx = tid; idx < TC_BN * 32; idx += 256) {
+    const int r = idx >> 5, c4 = idx & 31;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < nvalid) a = ldg4(kv + (size_t)(key0 + r) * ld + 2 * D + c4 * 4);
+    vt[r][c4 * 4] = a.x; vt[r][c4 * 4 + 1] = a.y; vt[r][c4 * 4 + 2] = a.z; vt[r][c4 * 4 + 3] = a.w;
+  }
+  __syncthreads();
+  // ---- V^T planes: (head, dim) rows of 64 keys
+  for (int idx = tid; idx < 8 * 16 * 8; idx += 256) {
+    const int kc = idx & 7, d = (idx >> 3) & 15, h = idx >> 7;
+    uint32_t hh[4], ll[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_pack(vt[8 * kc + 2 * i][16 * h + d], vt[8 * kc + 2 * i + 1][16 * h + d], hh[i], ll[i]);
+    const uint32_t off = TC_OFF_V + (uint32_t)(h * 2048) + tc::sw128_off(d, kc);
+    *reinterpret_cast<uint4*>(out + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+    *reinterpret_cast<uint4*>(out + 16384 + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+  }
+  // ---- key positions (scaled) and per-head max key norm
+  if (tid < TC_BN) {
+    float kx = INFINITY, ky = 0.f;                       // +inf => distance inf => bias -inf => p = 0 for padded keys
+    if (tid < nvalid) { kx = pos ? pos[2 * (size_t)(key0 + tid)] * pscale : 0.f; ky = pos ? pos[2 * (size_t)(key0 + tid) + 1] * pscale : 0.f; }
+    reinterpret_cast<float*>(out + TC_OFF_POS)[tid] = kx;
+    reinterpret_cast<float*>(out + TC_OFF_POS)[TC_BN + tid] = ky;
+  }
+  if (tid >= 64 && tid < 72) {
+    const int h = tid - 64;
+    float mx = 0.f;
+    for (int r = 0; r < TC_BN; ++r) mx = fmaxf(mx, ksq[r][h]);
+    reinterpret_cast<float*>(out + TC_OFF_KMAX)[h] = sqrtf(mx) * 1.0001f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- main kernel
+__global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc_kernel(const AttnTcParams p) {
+  using namespace tc;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* bp = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bars = base + TC_STAGES * TC_IMG;
+  // barrier map (8 B each): full[3] @0, empty[3] @24, S_ready[g][s] @48, P_ready[g][s] @80, O_done[g] @112, Q_ready[g] @128
+  const uint32_t bar_full = bars, bar_empty = bars + 24, bar_S = bars + 48, bar_P = bars + 80, bar_O = bars + 112, bar_Q = bars + 128;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bp + TC_STAGES * TC_IMG + 192);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // ---- locate this CTA's (segment, query tile)
+  int seg = -1, row0 = 0;
+  {
+    int acc = 0;
+    for (int s = 0; s < p.num_seg; ++s) {
+      const int a = p.qseg[s], b = p.qseg[s + 1];
+      const int nt = (b - a + TC_QT - 1) / TC_QT;
+      if ((int)blockIdx.x < acc + nt) { seg = s; row0 = a + ((int)blockIdx.x - acc) * TC_QT; break; }
+      acc += nt;
+    }
+  }
+  if (seg < 0) return;
+  const int qend = p.qseg[seg + 1];
+  const int split = blockIdx.y;
+  const int nb_seg = p.blk_ptr[seg + 1] - p.blk_ptr[seg];
+  const int per = (nb_seg + p.nsplit - 1) / p.nsplit;
+  const int b_lo = min(nb_seg, split * per), b_hi = min(nb_seg, b_lo + per);
+  const int nblk = b_hi - b_lo;
+  const uint8_t* img0 = p.img + (size_t)(p.blk_ptr[seg] + b_lo) * TC_IMG;
+
+  if (tid == 0) {
+    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 2 + 8); }
+    for (int i = 0; i < 4; ++i) { mbar_init(bar_S + 8 * i, 1); mbar_init(bar_P + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_O + 8 * i, 1); mbar_init(bar_Q + 8 * i, 4); }
+    mbar_fence_init();
+  }
+  if (warp == 10) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tm = *tmem_slot;
+
+  if (warp < 8) {
+    // =========================================================================== softmax groups
+    const int g = warp >> 2, wq = warp & 3;
+    const int row = row0 + wq * 32 + lane;
+    const bool rvalid = row < qend;
+    const uint32_t trow = tm + ((uint32_t)(wq * 32) << 16);
+    float qn[4];
+    // ---- Q: fp32 row -> scaled -> fp16 hi/lo -> TMEM (A operand of QK^T), and |q_h| for the lazy-max bound
+    {
+      const float* qp = p.q_qkv + (size_t)(rvalid ? row : row0) * p.ld_q + 64 * g;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t qh[8], ql[8];
+        float sq = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float4 v = ldg4(qp + 16 * i + 4 * c);
+          if (!rvalid) v = make_float4(0.f, 0.f, 0.f, 0.f);
+          v.x *= p.qscale; v.y *= p.qscale; v.z *= p.qscale; v.w *= p.qscale;
+          sq += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+          split_pack(v.x, v.y, qh[2 * c], ql[2 * c]);
+          split_pack(v.z, v.w, qh[2 * c + 1], ql[2 * c + 1]);
+        }
+        qn[i] = sqrtf(sq) * 1.0001f;
+        tmem_st8_nowait(trow + tc_qhi(4 * g + i), qh);
+        tmem_st8_nowait(trow + tc_qlo(4 * g + i), ql);
+      }
+      tmem_wait_st();
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_Q + 8 * g);
+    }
+    float qx = 0.f, qy = 0.f;
+    if (p.q_pos != nullptr && rvalid) { qx = p.q_pos[2 * (size_t)row] * p.pscale; qy = p.q_pos[2 * (size_t)row + 1] * p.pscale; }
+    const unsigned long long qx2 = pk2(qx, qx), qy2 = pk2(qy, qy);
+
+    float m[4];
+    unsigned long long lsum[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { m[i] = -INFINITY; lsum[i] = 0ull; }
+
+    for (int j = 0; j < nblk; ++j) {
+      const int st = j % TC_STAGES;
+      mbar_wait(bar_full + 8 * st, (uint32_t)((j / TC_STAGES) & 1));
+      // ---- negated distance bias of this row against the block's 64 keys (shared by the group's 4 heads)
+      unsigned long long nb[32];
+      float kmax[4];
+      {
+        const float* kp = reinterpret_cast<const float*>(bp + st * TC_IMG + TC_OFF_POS);
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          const float4 kx = *reinterpret_cast<const float4*>(kp + 4 * t);
+          const float4 ky = *reinterpret_cast<const float4*>(kp + TC_BN + 4 * t);
+          unsigned long long dx = sub2(qx2, pk2(kx.x, kx.y)), dy = sub2(qy2, pk2(ky.x, ky.y));
+          unsigned long long d2 = fma2(dx, dx, mul2(dy, dy));
+          nb[2 * t] = pk2(-tc_sqrt(lo32(d2)), -tc_sqrt(hi32(d2)));
+          dx = sub2(qx2, pk2(kx.z, kx.w)); dy = sub2(qy2, pk2(ky.z, ky.w));
+          d2 = fma2(dx, dx, mul2(dy, dy));
+          nb[2 * t + 1] = pk2(-tc_sqrt(lo32(d2)), -tc_sqrt(hi32(d2)));
+        }
+        const float4 km = *reinterpret_cast<const float4*>(bp + st * TC_IMG + TC_OFF_KMAX + 16 * g);
+        kmax[0] = km.x; kmax[1] = km.y; kmax[2] = km.z; kmax[3] = km.w;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_empty + 8 * st);            // this warp no longer reads the stage's position data
+
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int u = 4 * j + i, s = u & 1;
+        const uint32_t slot = trow + tc_slot(g, s);
+        mbar_wait(bar_S + 8 * (2 * g + s), (uint32_t)((u >> 1) & 1));
+        fence_after();
+        // ---- lazy reference max: only when the Cauchy-Schwarz bound says this block could overflow the current reference
+        const bool need = (j == 0) || (qn[i] * kmax[i] > m[i] + TC_TAU);
+        if (__any_sync(0xffffffffu, need)) {
+          float rmax = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld32_nowait(slot + 32 * c, r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+              const unsigned long long x = add2(pk2(__uint_as_float(r[2 * t]), __uint_as_float(r[2 * t + 1])), nb[16 * c + t]);
+              rmax = fmaxf(rmax, fmaxf(lo32(x), hi32(x)));
+            }
+          }
+          float sc = 1.0f;
+          if (j == 0) m[i] = rmax;
+          else if (rmax > m[i] + TC_TAU) { sc = tc_ex2(m[i] - rmax); m[i] = rmax; }
+          if (__any_sync(0xffffffffu, sc != 1.0f)) {
+            // rescale O_h and l of this row; every PV MMA on O_h issued so far has completed (in-order MMA pipe, S_ready waited)
+            uint32_t o[16];
+            tmem_ld16_nowait(trow + tc_ocol(4 * g + i), o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int t = 0; t < 16; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) * sc);
+            tmem_st16_nowait(trow + tc_ocol(4 * g + i), o);
+            lsum[i] = mul2(lsum[i], pk2(sc, sc));
+          }
+        }
+        const float mu = (m[i] == -INFINITY) ? 0.f : m[i];
+        const unsigned long long nmu2 = pk2(-mu, -mu);
+        const unsigned long long neg1 = pk2(-1.0f, -1.0f);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld32_nowait(slot + 32 * c, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              const int e = 16 * ks + 2 * t;                              // element pair (e, e+1) of this 32-key chunk
+              const unsigned long long x = add2(add2(pk2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), nb[16 * c + 8 * ks + t]), nmu2);
+              const float p0 = tc_ex2(lo32(x)), p1 = tc_ex2(hi32(x));
+              const unsigned long long pp = pk2(p0, p1);
+              lsum[i] = add2(lsum[i], pp);
+              const float h0 = __uint_as_float(__float_as_uint(p0) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(p1) & 0xffffe000u);
+              const unsigned long long ll = fma2(pk2(h0, h1), neg1, pp);  // p - hi, exact
+              hi[t] = tc_pack_h2(h0, h1);
+              lo[t] = tc_pack_h2(lo32(ll), hi32(ll));
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) { r[16 * ks + t] = hi[t]; r[16 * ks + 8 + t] = lo[t]; }
+          }
+          tmem_st32_nowait(slot + 32 * c, r);
+        }
+        tmem_wait_st();
+        fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_P + 8 * (2 * g + s));
+      }
+    }
+    // ---- epilogue: unnormalised O, reference max m, row sum l of this key split
+    if (nblk > 0) { mbar_wait(bar_O + 8 * g, 0); fence_after(); }
+    const size_t prow = (size_t)split * p.Nq + (size_t)row;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      if (nblk > 0) { tmem_ld32_nowait(trow + tc_ocol(4 * g) + 32 * c, r); tmem_wait_ld(); }
+      else {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) r[t] = 0u;
+      }
+      if (rvalid) {
+        float* op = p.Opart + prow * 128 + 64 * g + 32 * c;
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+          *reinterpret_cast<float4*>(op + 4 * t) = make_float4(__uint_as_float(r[4 * t]), __uint_as_float(r[4 * t + 1]),
+                                                               __uint_as_float(r[4 * t + 2]), __uint_as_float(r[4 * t + 3]));
+      }
+    }
+    if (rvalid) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        p.Mpart[prow * 8 + 4 * g + i] = m[i];
+        p.Lpart[prow * 8 + 4 * g + i] = lo32(lsum[i]) + hi32(lsum[i]);
+      }
+    }
+  } else if (warp < 10) {
+    // =========================================================================== MMA issuers (one per head group)
+    const int g = warp - 8;
+    if (nblk > 0 && elect_one()) {
+      const uint32_t id64 = idesc_f16(128, 64), id16 = idesc_f16(128, 16);
+      const int total = 4 * nblk;
+      mbar_wait(bar_Q + 8 * g, 0);
+      fence_after();
+      auto issue_qk = [&](int u) {
+        const int b = u >> 2, i = u & 3, st = b % TC_STAGES;
+        if (i == 0) { mbar_wait(bar_full + 8 * st, (uint32_t)((b / TC_STAGES) & 1)); fence_after(); }
+        const uint32_t d = tm + tc_slot(g, u & 1);
+        const uint32_t kb = base + st * TC_IMG + 8192 * g + 32 * i;
+        mma_ts(d, tm + tc_qhi(4 * g + i), desc_sw128(kb), id64, 0);
+        mma_ts(d, tm + tc_qlo(4 * g + i), desc_sw128(kb), id64, 1);
+        mma_ts(d, tm + tc_qhi(4 * g + i), desc_sw128(kb + 16384), id64, 1);
+        mma_commit(bar_S + 8 * (2 * g + (u & 1)));
+      };
+      issue_qk(0);
+      if (total > 1) issue_qk(1);
+      for (int u = 0; u < total; ++u) {
+        const int b = u >> 2, i = u & 3, st = b % TC_STAGES, h = 4 * g + i;
+        mbar_wait(bar_P + 8 * (2 * g + (u & 1)), (uint32_t)((u >> 1) & 1));
+        fence_after();
+        const uint32_t vb = base + st * TC_IMG + TC_OFF_V + 2048 * h;
+        const uint32_t ps = tm + tc_slot(g, u & 1);
+        const uint32_t od = tm + tc_ocol(h);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          mma_ts(od, ps + 16 * ks, desc_sw128(vb + 32 * ks), id16, (b > 0 || ks > 0) ? 1u : 0u);
+          mma_ts(od, ps + 16 * ks + 8, desc_sw128(vb + 32 * ks), id16, 1);
+          mma_ts(od, ps + 16 * ks, desc_sw128(vb + 16384 + 32 * ks), id16, 1);
+        }
+        if (i == 3) mma_commit(bar_empty + 8 * st);                  // every MMA reading this stage has been issued
+        if (u + 2 < total) issue_qk(u + 2);
+      }
+      mma_commit(bar_O + 8 * g);
+    }
+    __syncwarp();
+  } else {
+    // =========================================================================== loader (cp.async.bulk, 3-stage ring)
+    if (elect_one()) {
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j % TC_STAGES;
+        mbar_wait(bar_empty + 8 * st, (uint32_t)(((j / TC_STAGES) & 1) ^ 1));
+        mbar_arrive_expect_tx(bar_full + 8 * st, TC_IMG_USED);
+        const uint8_t* src = img0 + (size_t)j * TC_IMG;
+        const uint32_t dst = base + st * TC_IMG;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) bulk_g2s(dst + 16384 * c, src + 16384 * c, 16384, bar_full + 8 * st);
+        bulk_g2s(dst + 65536, src + 65536, TC_IMG_USED - 65536, bar_full + 8 * st);
+      }
+    }
+    __syncwarp();
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 10) tmem_dealloc(tm, 512);
+}
+
+static inline size_t tc_al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int attn_tc_nsplit(int Nq, int Nkv, int num_seg) {
+  const int tiles = (Nq + TC_QT - 1) / TC_QT + num_seg;
+  int s = (148 * 8 + tiles - 1) / tiles;                       // aim for >= ~8 CTAs of work per SM
+  const int avg_blocks = (Nkv / (num_seg > 0 ? num_seg : 1)) / TC_BN;
+  const int max_s = avg_blocks / 8 > 1 ? avg_blocks / 8 : 1;   // at least ~8 key blocks per CTA
+  if (s > max_s) s = max_s;
+  if (s > 16) s = 16;
+  if (s < 1) s = 1;
+  return s;
+}
+
+size_t attn_tc_work_bytes(int Nq, int Nkv, int D, int heads, int num_seg) {
+  const int ns = attn_tc_nsplit(Nq, Nkv, num_seg);
+  const size_t nblk_max = (size_t)(Nkv + TC_BN - 1) / TC_BN + (size_t)num_seg;
+  size_t b = 1024;
+  b += tc_al256(nblk_max * TC_IMG) + 1024;
+  b += tc_al256((size_t)(num_seg + 1) * 4);
+  b += tc_al256((size_t)ns * Nq * D * 4);
+  b += 2 * tc_al256((size_t)ns * Nq * heads * 4);
+  return b;
+}
+
+// defined in attention.cu
+void attn_launch_combine(const float* Opart, const float* Mpart, const float* Lpart, int nsplit, int Nq, int D, int heads,
+                         float* out, int ldo, cudaStream_t s);
+
+int attn_tc_launch(const float* q_qkv, int ld_q, const float* q_pos, const int* qseg_ptr, int Nq,
+                   const float* kv_qkv, int ld_kv, const float* kv_pos, const int* kseg_ptr, int Nkv,
+                   int num_seg, float temperature, float* out, int ldo, void* work, size_t work_bytes, cudaStream_t s) {
+  constexpr int D = 128, heads = 8;
+  if (work_bytes < attn_tc_work_bytes(Nq, Nkv, D, heads, num_seg)) return DGDM_ERR_INVALID;
+  const int ns = attn_tc_nsplit(Nq, Nkv, num_seg);
+  const size_t nblk_max = (size_t)(Nkv + TC_BN - 1) / TC_BN + (size_t)num_seg;
+  uint8_t* w = (uint8_t*)(((uintptr_t)work + 1023) & ~(uintptr_t)1023);
+  uint8_t* img = w; w += tc_al256(nblk_max * TC_IMG);
+  int* blk_ptr = (int*)w; w += tc_al256((size_t)(num_seg + 1) * 4);
+  float* Opart = (float*)w; w += tc_al256((size_t)ns * Nq * D * 4);
+  float* Mpart = (float*)w; w += tc_al256((size_t)ns * Nq * heads * 4);
+  float* Lpart = (float*)w;
+  const float LOG2E = 1.4426950408889634f;
+  const float pscale = LOG2E / temperature;
+  attn_tc_blkptr_kernel<<<1, 32, 0, s>>>(kseg_ptr, num_seg, blk_ptr);
+  attn_tc_prep_kernel<<<(unsigned)nblk_max, 256, 0, s>>>(kv_qkv, ld_kv, kv_pos, kseg_ptr, blk_ptr, num_seg, pscale, img);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(spatial_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM) != cudaSuccess) return DGDM_ERR_LAUNCH;
+    attr_set = true;
+  }
+  AttnTcParams p;
+  p.q_qkv = q_qkv; p.ld_q = ld_q; p.q_pos = q_pos; p.qseg = qseg_ptr; p.kseg = kseg_ptr; p.num_seg = num_seg; p.Nq = Nq; p.nsplit = ns;
+  p.img = img; p.blk_ptr = blk_ptr; p.qscale = LOG2E / 4.0f; p.pscale = pscale;
+  p.Opart = Opart; p.Mpart = Mpart; p.Lpart = Lpart;
+  const int tiles = (Nq + TC_QT - 1) / TC_QT + num_seg;
+  spatial_attn_tc_kernel<<<dim3(tiles, ns, 1), TC_THREADS, TC_SMEM, s>>>(p);
+  attn_launch_combine(Opart, Mpart, Lpart, ns, Nq, D, heads, out, ldo, s);
+  if (cudaGetLastError() != cudaSuccess) return DGDM_ERR_LAUNCH;
+  return DGDM_OK;
+}
+
+}  // namespace dgdm

@@ -135,7 +135,9 @@ int dgdm_spatial_pe_add(const float* X, int ldx, const float* pos, const int* se
  * kv_pos/kv_qkv allow the keys/values to come from a different (all-gathered) node set for node-partitioned
  * graphs: queries rows [0,Nq) use key segment [kseg_ptr[g], kseg_ptr[g+1]) of the kv arrays, with g = the
  * query's segment in qseg_ptr.  work: dgdm_spatial_attention_work_bytes(...) bytes.
- * precise != 0 selects the 3-pass split-fp16 tensor path (~fp32 accuracy); 0 = single-pass fp16 operands. */
+ * precise: 1 = product path, 3-term split-fp16 products (~fp32 accuracy): the tcgen05/TMEM kernel when D == 128 and heads == 8
+ *             (DGDM-Base), else the mma.sync kernel; 2 = force the 3-term mma.sync kernel (comparison baseline);
+ *          0 = single-pass fp16 operands on mma.sync (~1e-3, comparison only). head_dim must be 16. */
 size_t dgdm_spatial_attention_work_bytes(int Nq, int Nkv, int D, int heads, int num_seg);
 int dgdm_spatial_attention(const float* q_qkv, int ld_q, const float* q_pos, const int* qseg_ptr, int Nq,
                            const float* kv_qkv, int ld_kv, const float* kv_pos, const int* kseg_ptr, int Nkv,

@@ -8,7 +8,7 @@
 //   O_h += P V_h          tcgen05.mma M=128 N=16 K=16 x 4 K-steps, A = P (TMEM), B = V_h^T tile (smem), accumulator in TMEM
 // All products use the 3-term split (hi*hi + lo*hi + hi*lo) -> fp32-class results (same arithmetic as the mma.sync kernel).
 //
-// CTA = 352 threads: warps 0-3 softmax group 0 (heads 0-3), warps 4-7 softmax group 1 (heads 4-7) — thread = query row, so the
+// CTA = 384 threads: warps 0-3 softmax group 0 (heads 0-3), warps 4-7 softmax group 1 (heads 4-7) — thread = query row, so the
 // distance bias of a (row, key block) is computed once into registers and reused by the group's 4 heads; warps 8/9 issue the MMAs
 // for group 0/1 (one elected thread each); warp 10 streams pre-swizzled K / V^T / position block images global -> smem with
 // cp.async.bulk (TMA engine) through a 3-stage mbarrier ring. TMEM (512 columns): 4 S/P slots x 64 | O 8 x 16 | Q hi 8 x 8 | Q lo 8 x 8.
@@ -27,9 +27,9 @@ constexpr int TC_OFF_POS = 65536;              // kx[64], ky[64] (pre-scaled by 
 constexpr int TC_OFF_KMAX = 65536 + 512;       // max_j |k_j,h| per head (8 floats)
 constexpr int TC_IMG_USED = 65536 + 512 + 32;  // bytes actually copied per block
 constexpr int TC_STAGES = 3;
-constexpr int TC_THREADS = 352;
+constexpr int TC_THREADS = 384;                 // 3 warpgroups: softmax 0, softmax 1, {MMA 0, MMA 1, loader, idle}
 constexpr int TC_SMEM = TC_STAGES * TC_IMG + 1024 + 256;
-constexpr float TC_TAU = 8.0f;                 // lazy-max slack (log2 units): p <= 2^8 stays exact in the fp16 hi/lo split
+constexpr float TC_TAU = 12.0f;                // lazy-max slack (log2 units): p <= 2^12 is far inside the fp16 range of the hi plane
 
 // TMEM column map
 __device__ __forceinline__ constexpr uint32_t tc_slot(int g, int s) { return (uint32_t)((2 * g + s) * 64); }
@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc_kernel(const At
 
   if (warp < 8) {
     // =========================================================================== softmax groups
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");      // registers handed over by the MMA / loader warpgroup
     const int g = warp >> 2, wq = warp & 3;
     const int row = row0 + wq * 32 + lane;
     const bool rvalid = row < qend;
@@ -240,9 +241,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc_kernel(const At
 #pragma unroll
     for (int i = 0; i < 4; ++i) { m[i] = -INFINITY; lsum[i] = 0ull; }
 
+    // S of the unit being processed lives in registers (ra = keys 0-31, rb = keys 32-63 of the block); the loads for the NEXT
+    // unit are issued while the current one is still in the exp2 / split phase, so neither the S_ready wait nor the TMEM
+    // read latency sits on the critical path.
+    uint32_t ra[32], rb[32];
+    const int total = 4 * nblk;
+    if (nblk > 0) {
+      mbar_wait_parked(bar_S + 8 * (2 * g), 0);
+      fence_after();
+      tmem_ld32_nowait(trow + tc_slot(g, 0), ra);
+      tmem_ld32_nowait(trow + tc_slot(g, 0) + 32, rb);
+    }
+    const unsigned long long neg1 = pk2(-1.0f, -1.0f);
+    // exp2 + fp16 hi/lo split of one 32-key chunk held in r (in place), accumulating the row sum
+    auto softmax_chunk = [&](uint32_t* r, const unsigned long long* nbc, unsigned long long nmu2, unsigned long long& ls) {
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int e = 16 * ks + 2 * t;                              // element pair (e, e+1) of this 32-key chunk
+          const unsigned long long x = add2(add2(pk2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), nbc[8 * ks + t]), nmu2);
+          const float p0 = tc_ex2(lo32(x)), p1 = tc_ex2(hi32(x));
+          const unsigned long long pp = pk2(p0, p1);
+          ls = add2(ls, pp);
+          const float h0 = __uint_as_float(__float_as_uint(p0) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(p1) & 0xffffe000u);
+          const unsigned long long ll = fma2(pk2(h0, h1), neg1, pp);  // p - hi, exact
+          hi[t] = tc_pack_h2(h0, h1);
+          lo[t] = tc_pack_h2(lo32(ll), hi32(ll));
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { r[16 * ks + t] = hi[t]; r[16 * ks + 8 + t] = lo[t]; }
+      }
+    };
+
     for (int j = 0; j < nblk; ++j) {
       const int st = j % TC_STAGES;
-      mbar_wait(bar_full + 8 * st, (uint32_t)((j / TC_STAGES) & 1));
+      mbar_wait_parked(bar_full + 8 * st, (uint32_t)((j / TC_STAGES) & 1));
       // ---- negated distance bias of this row against the block's 64 keys (shared by the group's 4 heads)
       unsigned long long nb[32];
       float kmax[4];
@@ -269,22 +304,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc_kernel(const At
       for (int i = 0; i < 4; ++i) {
         const int u = 4 * j + i, s = u & 1;
         const uint32_t slot = trow + tc_slot(g, s);
-        mbar_wait(bar_S + 8 * (2 * g + s), (uint32_t)((u >> 1) & 1));
-        fence_after();
+        const uint32_t nslot = trow + tc_slot(g, s ^ 1);
+        tmem_wait_ld();                                           // ra / rb of this unit (issued one unit ago)
         // ---- lazy reference max: only when the Cauchy-Schwarz bound says this block could overflow the current reference
         const bool need = (j == 0) || (qn[i] * kmax[i] > m[i] + TC_TAU);
         if (__any_sync(0xffffffffu, need)) {
           float rmax = -INFINITY;
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t r[32];
-            tmem_ld32_nowait(slot + 32 * c, r);
-            tmem_wait_ld();
-#pragma unroll
-            for (int t = 0; t < 16; ++t) {
-              const unsigned long long x = add2(pk2(__uint_as_float(r[2 * t]), __uint_as_float(r[2 * t + 1])), nb[16 * c + t]);
-              rmax = fmaxf(rmax, fmaxf(lo32(x), hi32(x)));
-            }
+          for (int t = 0; t < 16; ++t) {
+            const unsigned long long xa = add2(pk2(__uint_as_float(ra[2 * t]), __uint_as_float(ra[2 * t + 1])), nb[t]);
+            const unsigned long long xb = add2(pk2(__uint_as_float(rb[2 * t]), __uint_as_float(rb[2 * t + 1])), nb[16 + t]);
+            rmax = fmaxf(rmax, fmaxf(fmaxf(lo32(xa), hi32(xa)), fmaxf(lo32(xb), hi32(xb))));
           }
           float sc = 1.0f;
           if (j == 0) m[i] = rmax;
@@ -302,40 +332,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc_kernel(const At
         }
         const float mu = (m[i] == -INFINITY) ? 0.f : m[i];
         const unsigned long long nmu2 = pk2(-mu, -mu);
-        const unsigned long long neg1 = pk2(-1.0f, -1.0f);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t r[32];
-          tmem_ld32_nowait(slot + 32 * c, r);
-          tmem_wait_ld();
-#pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            uint32_t hi[8], lo[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              const int e = 16 * ks + 2 * t;                              // element pair (e, e+1) of this 32-key chunk
-              const unsigned long long x = add2(add2(pk2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), nb[16 * c + 8 * ks + t]), nmu2);
-              const float p0 = tc_ex2(lo32(x)), p1 = tc_ex2(hi32(x));
-              const unsigned long long pp = pk2(p0, p1);
-              lsum[i] = add2(lsum[i], pp);
-              const float h0 = __uint_as_float(__float_as_uint(p0) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(p1) & 0xffffe000u);
-              const unsigned long long ll = fma2(pk2(h0, h1), neg1, pp);  // p - hi, exact
-              hi[t] = tc_pack_h2(h0, h1);
-              lo[t] = tc_pack_h2(lo32(ll), hi32(ll));
-            }
-#pragma unroll
-            for (int t = 0; t < 8; ++t) { r[16 * ks + t] = hi[t]; r[16 * ks + 8 + t] = lo[t]; }
-          }
-          tmem_st32_nowait(slot + 32 * c, r);
+        softmax_chunk(ra, nb, nmu2, lsum[i]);
+        tmem_st32_nowait(slot, ra);
+        if (u + 1 < total) {                                      // prefetch the first half of the next unit's S into ra
+          mbar_wait_parked(bar_S + 8 * (2 * g + (s ^ 1)), (uint32_t)(((u + 1) >> 1) & 1));
+          fence_after();
+          tmem_ld32_nowait(nslot, ra);
         }
+        softmax_chunk(rb, nb + 16, nmu2, lsum[i]);
+        tmem_st32_nowait(slot + 32, rb);
         tmem_wait_st();
         fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_P + 8 * (2 * g + s));
+        if (u + 1 < total) tmem_ld32_nowait(nslot + 32, rb);      // second half of the next unit
       }
     }
     // ---- epilogue: unnormalised O, reference max m, row sum l of this key split
-    if (nblk > 0) { mbar_wait(bar_O + 8 * g, 0); fence_after(); }
+    if (nblk > 0) { mbar_wait_parked(bar_O + 8 * g, 0); fence_after(); }
     const size_t prow = (size_t)split * p.Nq + (size_t)row;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
@@ -360,17 +374,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc_kernel(const At
         p.Lpart[prow * 8 + 4 * g + i] = lo32(lsum[i]) + hi32(lsum[i]);
       }
     }
-  } else if (warp < 10) {
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp < 10) {
     // =========================================================================== MMA issuers (one per head group)
     const int g = warp - 8;
     if (nblk > 0 && elect_one()) {
       const uint32_t id64 = idesc_f16(128, 64), id16 = idesc_f16(128, 16);
       const int total = 4 * nblk;
-      mbar_wait(bar_Q + 8 * g, 0);
+      mbar_wait_parked(bar_Q + 8 * g, 0);
       fence_after();
       auto issue_qk = [&](int u) {
         const int b = u >> 2, i = u & 3, st = b % TC_STAGES;
-        if (i == 0) { mbar_wait(bar_full + 8 * st, (uint32_t)((b / TC_STAGES) & 1)); fence_after(); }
+        if (i == 0) { mbar_wait_parked(bar_full + 8 * st, (uint32_t)((b / TC_STAGES) & 1)); fence_after(); }
         const uint32_t d = tm + tc_slot(g, u & 1);
         const uint32_t kb = base + st * TC_IMG + 8192 * g + 32 * i;
         mma_ts(d, tm + tc_qhi(4 * g + i), desc_sw128(kb), id64, 0);
@@ -382,7 +398,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc_kernel(const At
       if (total > 1) issue_qk(1);
       for (int u = 0; u < total; ++u) {
         const int b = u >> 2, i = u & 3, st = b % TC_STAGES, h = 4 * g + i;
-        mbar_wait(bar_P + 8 * (2 * g + (u & 1)), (uint32_t)((u >> 1) & 1));
+        mbar_wait_parked(bar_P + 8 * (2 * g + (u & 1)), (uint32_t)((u >> 1) & 1));
         fence_after();
         const uint32_t vb = base + st * TC_IMG + TC_OFF_V + 2048 * h;
         const uint32_t ps = tm + tc_slot(g, u & 1);
@@ -399,12 +415,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc_kernel(const At
       mma_commit(bar_O + 8 * g);
     }
     __syncwarp();
-  } else {
+    } else if (warp == 10) {
     // =========================================================================== loader (cp.async.bulk, 3-stage ring)
     if (elect_one()) {
       for (int j = 0; j < nblk; ++j) {
         const int st = j % TC_STAGES;
-        mbar_wait(bar_empty + 8 * st, (uint32_t)(((j / TC_STAGES) & 1) ^ 1));
+        mbar_wait_parked(bar_empty + 8 * st, (uint32_t)(((j / TC_STAGES) & 1) ^ 1));
         mbar_arrive_expect_tx(bar_full + 8 * st, TC_IMG_USED);
         const uint8_t* src = img0 + (size_t)j * TC_IMG;
         const uint32_t dst = base + st * TC_IMG;
@@ -414,6 +430,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc_kernel(const At
       }
     }
     __syncwarp();
+    }
   }
   fence_before();
   __syncthreads();

@@ -32,6 +32,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (++spins > (1u << 26)) { asm volatile("trap;"); }
   }
 }
+// try_wait with a suspend-time hint: the thread is parked by the hardware for up to `ns` instead of spinning, so a waiting
+// producer / MMA-issuer warp does not steal issue slots from the compute warps that share its scheduler.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity), "r"(ns) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    if (++spins > (1u << 20)) { asm volatile("trap;"); }
+  }
+}
 
 // ---------------------------------------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

@@ -2,129 +2,74 @@
 //
 //   C[M,N] = epilogue( A[M,K] (fp32) @ W[N,K]^T )     N <= 512, whole output rows live in TMEM (512 columns)
 //
-// Precision: A and W are each split into two fp16 planes (hi, lo); D += Ahi*Whi + Alo*Whi + Ahi*Wlo with fp32
+// Precision: A and W are each split into two fp16 planes (hi, lo); D += Alo*Whi + Ahi*Wlo + Ahi*Whi with fp32
 // accumulation in TMEM (3 tcgen05.mma kind::f16 per K-step) -> ~2^-21 relative, i.e. fp32-class results.
-// Layout: one CTA = 128 rows x all N columns. K is walked in 64-wide blocks, 2-stage smem ring:
-//   A block: fp32 global -> registers (128-bit coalesced) -> hi/lo fp16 -> smem, K-major SWIZZLE_128B canonical layout
-//   W block: pre-split fp16 planes [N,Kpad] -> cp.async 16 B -> same canonical layout
-// One elected thread issues the MMAs; tcgen05.commit on an mbarrier frees the stage. N > 256 is covered by
-// N-passes of <=256 columns into adjacent TMEM column ranges. The epilogue keeps one output row per thread
-// (TMEM lane == row), so LayerNorm statistics are thread-local; global I/O goes through a per-warp smem
-// transpose so that every global access is a full 128-byte row segment.
-#include "common.cuh"
+//
+// Persistent, warp-specialised kernel: one CTA per SM walks the 128-row tiles m = blockIdx.x, +gridDim.x, ...
+//   warps 0-3   epilogue: TMEM lane == output row == thread, so LayerNorm statistics are thread-local; global I/O goes
+//               through a per-warp 32x32 smem transpose so that every global access is a full 128-byte row segment.
+//               With N <= 256 there are two 256-column accumulator buffers and the epilogue of tile t overlaps the
+//               main loop of tile t+1; with N > 256 the single 512-column buffer serialises MMA and epilogue, but the
+//               loads / conversions of the next tile still run ahead.
+//   warps 4-11  A converters: fp32 global rows (128-bit coalesced, next K-block prefetched into registers before the
+//               current one is converted -> ~64 KB of loads in flight per SM) -> hi/lo fp16 -> smem ring in the K-major
+//               SWIZZLE_128B canonical layout.
+//   warp 12     W producer: one elected lane streams the pre-swizzled weight K-block images (dgdm_split_weight_f16) with
+//               cp.async.bulk (TMA engine) into the W ring; completion is counted in bytes on an mbarrier.
+//   warp 13     MMA issuer: one elected lane; tcgen05.commit frees ring slots and publishes finished accumulators.
+// N > 256 is covered by column chunks of <= 256 into adjacent TMEM column ranges (one W ring unit per chunk).
+#include "tc05.cuh"
 
 namespace dgdm {
+using namespace tc;
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_NCHUNK = 256;
-constexpr int GEMM_THREADS = 256;
-constexpr int A_PLANE_BYTES = GEMM_BM * GEMM_BK * 2;        // 16 KB
-constexpr int W_PLANE_BYTES = GEMM_NCHUNK * GEMM_BK * 2;    // 32 KB
-constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * W_PLANE_BYTES;   // 96 KB
-constexpr int GEMM_SMEM = 2 * STAGE_BYTES + 1024 /*align*/ + 64 /*barriers*/;
+constexpr int GEMM_EPI_WARPS = 4;
+constexpr int GEMM_CONV_WARPS = 8;
+constexpr int GEMM_CONV_THREADS = GEMM_CONV_WARPS * 32;
+constexpr int GEMM_THREADS = (GEMM_EPI_WARPS + GEMM_CONV_WARPS + 2) * 32;     // 448
+constexpr int A_PLANE_BYTES = GEMM_BM * GEMM_BK * 2;                           // 16 KB
+constexpr int A_SLOT_BYTES = 2 * A_PLANE_BYTES;                                // 32 KB (hi | lo)
+constexpr int GEMM_RING_BYTES = 192 * 1024;                                    // A slots + W slots
+constexpr int TR_STRIDE = 36;                                                  // floats; conflict-free for 128-bit accesses
+constexpr int GEMM_STAGING_BYTES = GEMM_EPI_WARPS * 32 * TR_STRIDE * 4;        // 18432
+constexpr int GEMM_MAX_SLOTS = 4;
+constexpr int GEMM_VEC_BYTES = 6 * 512 * 4;                                    // bias, ln1 g/b, ln2 g/b, dot_w
+constexpr int GEMM_SMEM = GEMM_RING_BYTES + GEMM_STAGING_BYTES + GEMM_VEC_BYTES + 256 /*barriers*/ + 1024 /*align*/;
 
-// ---- PTX wrappers --------------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-// bounded wait: a wrong descriptor must not hang the GPU — after ~2^28 polls we trap.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 28)) { asm volatile("trap;"); }
-  }
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
-  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
-      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
-        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
-        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// K-major SWIZZLE_128B canonical layout: 8-row x 128-byte atoms, 1024 B apart (SBO); LBO unused.
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address, bits [0,14)
-  d |= (uint64_t)1 << 16;                         // leading byte offset (ignored for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset = 1024 B
-  d |= (uint64_t)1 << 46;                         // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
-  return d;
-}
-// byte offset of 16-byte chunk `c` (0..7) of row `r` inside a [rows x 64 fp16] SW128 tile
-__device__ __forceinline__ uint32_t sw128_off(int r, int c) {
-  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
-}
+struct GemmSched {
+  int na, nw;              // ring depths
+  int w_slot_bytes;        // bytes per W ring slot (2 planes x chunk rows x 128 B)
+  int nbuf;                // accumulator buffers in TMEM (2 when N <= 256, else 1)
+  int ntiles;
+  long long w_plane_stride;   // bytes between the hi and lo plane of one K-block image ( = total weight rows x 128 )
+};
 
 __device__ __forceinline__ uint32_t pack_half2(__half a, __half b) {
   return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
-__device__ __forceinline__ void split4(float4 v, float s, uint2& hi, uint2& lo) {
-  float x0 = v.x * s, x1 = v.y * s, x2 = v.z * s, x3 = v.w * s;
-  __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1), h2 = __float2half_rn(x2), h3 = __float2half_rn(x3);
-  __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
-  __half l2 = __float2half_rn(x2 - __half2float(h2)), l3 = __float2half_rn(x3 - __half2float(h3));
-  hi = make_uint2(pack_half2(h0, h1), pack_half2(h2, h3));
-  lo = make_uint2(pack_half2(l0, l1), pack_half2(l2, l3));
+__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+// 4 fp32 -> packed fp16 hi (round to nearest) and lo = fp16(x - hi): cvt.rn.f16x2.f32 pairs, 3 instructions per element
+__device__ __forceinline__ void split4(float4 v, uint2& hi, uint2& lo) {
+  const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+  const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+  const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+  hi = make_uint2(h2_bits(h01), h2_bits(h23));
+  lo = make_uint2(h2_bits(l01), h2_bits(l23));
 }
 
-// ---- per-warp 32x32 transposing I/O through smem (stride 36 floats, conflict-free for 128-bit accesses) ----
-constexpr int TR_STRIDE = 36;
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  tmem_ld32_nowait(taddr, reinterpret_cast<uint32_t*>(v));
+  tmem_wait_ld();
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+  tmem_st32_nowait(taddr, reinterpret_cast<const uint32_t*>(v));
+  tmem_wait_st();
+}
+
+// ---- per-warp 32x32 transposing I/O through smem ----
 // thread-row-owned regs v[32] (row = lane) -> coalesced global store of rows [row0, row0+32), cols [c0, c0+32)
 __device__ __forceinline__ void warp_store_tile(float* st, const float* v, float* G, int ldg, int row0, int c0,
                                                 int M, int N, int lane) {
@@ -159,208 +104,348 @@ __device__ __forceinline__ void warp_load_tile(float* st, float* v, const float*
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16x2_kernel(const dgdm_gemm_params p, uint32_t tmem_cols) {
+// Column vectors of the epilogue staged once per CTA in shared memory (zero / one filled when absent) so that the element
+// loops below are branch-free FFMA chains fed by broadcast LDS.128 instead of per-element predicated global loads.
+struct EpiVec { const float* bias; const float* g1; const float* b1; const float* g2; const float* b2; const float* dotw; };
+constexpr int EPI_VEC_FLOATS = 6 * 512;
+
+__device__ __forceinline__ void lds_row32(const float* s, float* o) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 q = *reinterpret_cast<const float4*>(s + 4 * j);
+    o[4 * j] = q.x; o[4 * j + 1] = q.y; o[4 * j + 2] = q.z; o[4 * j + 3] = q.w;
+  }
+}
+
+// Row-wise epilogue of one 128-row tile by one epilogue warp (32 rows): thread = row, accumulator row in TMEM at t_row.
+// Every feature test is warp-uniform and hoisted out of the 32-element loops.
+__device__ __forceinline__ void epilogue_rows(const dgdm_gemm_params& p, const EpiVec& ev, float* st, uint32_t t_row, int row0, int lane) {
+  const int row = row0 + lane;
+  const float inv_scale = 1.0f / p.a_scale;
+  const bool has_ln1 = p.ln1_g != nullptr, has_ln2 = p.ln2_g != nullptr;
+  const bool writeback = has_ln1 || has_ln2;
+  const float invN = 1.0f / (float)p.N;
+  float v[32], t[32];
+  float sum = 0.f, dot = 0.f;
+
+  auto finish = [&](int c0) {   // v holds the post-LN values of columns [c0, c0+32)
+    apply_act_chunk<32>(v, p.act_post);
+    if (p.r_post != nullptr) {
+      warp_load_tile(st, t, p.r_post, p.ld_r_post, row0, c0, p.M, p.N, lane);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += t[j];
+    }
+    if (p.dot_w != nullptr) {        // columns >= N hold zeros in ev.dotw
+      lds_row32(ev.dotw + c0, t);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) dot = fmaf(v[j], t[j], dot);
+    }
+    if (p.C != nullptr) warp_store_tile(st, v, p.C, p.ldc, row0, c0, p.M, p.N, lane);
+  };
+  auto normalise = [&](int c0, const float* g, const float* b, float mean, float rstd) {
+    lds_row32(g + c0, t);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = (v[j] - mean) * rstd * t[j];
+    lds_row32(b + c0, t);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += t[j];
+    if (c0 + 32 > p.N) {
+#pragma unroll
+      for (int j = 16; j < 32; ++j) v[j] = 0.f;
+    }
+  };
+  auto sq_dev = [&](int c0, float mean, float& ss) {
+    if (c0 + 32 > p.N) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { const float d = v[j] - mean; ss = fmaf(d, d, ss); }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; ss = fmaf(d, d, ss); }
+    }
+  };
+
+  // pass 1: v = acc/scale + bias (+row_bias) (+r_pre); act_pre
+  for (int c0 = 0; c0 < p.N; c0 += 32) {
+    tmem_ld32(t_row + (uint32_t)c0, v);
+    if (p.bias != nullptr) {
+      lds_row32(ev.bias + c0, t);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], inv_scale, t[j]);
+    } else if (p.a_scale != 1.0f) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= inv_scale;
+    }
+    if (p.row_bias != nullptr) {
+      const int rbi = row < p.M ? p.row_bias_index[row] : 0;
+      const float* rb = p.row_bias + (size_t)rbi * p.ld_row_bias + c0;
+      const int nv = (c0 + 32 > p.N) ? 4 : 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < nv) {
+          const float4 q = ldg4(rb + 4 * j);
+          v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+        }
+      }
+    }
+    if (p.r_pre != nullptr) {
+      warp_load_tile(st, t, p.r_pre, p.ld_r_pre, row0, c0, p.M, p.N, lane);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += t[j];
+    }
+    if (p.act_pre != DGDM_ACT_NONE) apply_act_chunk<32>(v, p.act_pre);
+    if (c0 + 32 > p.N) {          // N % 16 == 0: only the upper half of the last chunk can lie outside the row
+#pragma unroll
+      for (int j = 16; j < 32; ++j) v[j] = 0.f;
+    }
+    if (writeback) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sum += v[j];
+      tmem_st32(t_row + (uint32_t)c0, v);
+    } else finish(c0);
+  }
+  if (writeback) {
+    const float* g = has_ln1 ? ev.g1 : ev.g2;
+    const float* b = has_ln1 ? ev.b1 : ev.b2;
+    float mean = sum * invN, ss = 0.f;
+    for (int c0 = 0; c0 < p.N; c0 += 32) {
+      tmem_ld32(t_row + (uint32_t)c0, v);
+      sq_dev(c0, mean, ss);
+    }
+    float rstd = rsqrtf(ss * invN + p.ln_eps);
+    if (has_ln1 && has_ln2) {
+      float sum2 = 0.f;
+      for (int c0 = 0; c0 < p.N; c0 += 32) {
+        tmem_ld32(t_row + (uint32_t)c0, v);
+        normalise(c0, g, b, mean, rstd);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum2 += v[j];
+        tmem_st32(t_row + (uint32_t)c0, v);
+      }
+      mean = sum2 * invN; ss = 0.f;
+      for (int c0 = 0; c0 < p.N; c0 += 32) {
+        tmem_ld32(t_row + (uint32_t)c0, v);
+        sq_dev(c0, mean, ss);
+      }
+      rstd = rsqrtf(ss * invN + p.ln_eps);
+      g = ev.g2; b = ev.b2;
+    }
+    for (int c0 = 0; c0 < p.N; c0 += 32) {
+      tmem_ld32(t_row + (uint32_t)c0, v);
+      normalise(c0, g, b, mean, rstd);
+      finish(c0);
+    }
+  }
+  if (p.dot_out != nullptr && row < p.M) p.dot_out[row] = apply_act(dot + p.dot_b, p.dot_act);
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16x2_kernel(const dgdm_gemm_params p, const GemmSched sc) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bar_base = base + 2 * STAGE_BYTES;     // [0],[1]: stage free; [2]: all MMAs done
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 2 * STAGE_BYTES + 32);
+  const uint32_t a_ring = base;
+  const uint32_t w_ring = base + (uint32_t)sc.na * A_SLOT_BYTES;
+  float* staging = reinterpret_cast<float*>(base_ptr + GEMM_RING_BYTES);
+  float* vecs = reinterpret_cast<float*>(base_ptr + GEMM_RING_BYTES + GEMM_STAGING_BYTES);
+  const uint32_t bar_base = base + GEMM_RING_BYTES + GEMM_STAGING_BYTES + GEMM_VEC_BYTES;
+  const uint32_t bar_full_a = bar_base, bar_empty_a = bar_base + 32, bar_full_w = bar_base + 64, bar_empty_w = bar_base + 96;
+  const uint32_t bar_acc_full = bar_base + 128, bar_acc_empty = bar_base + 144;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + GEMM_RING_BYTES + GEMM_STAGING_BYTES + GEMM_VEC_BYTES + 192);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * GEMM_BM;
   const int nkb = (p.K + GEMM_BK - 1) / GEMM_BK;
-  const int npass = (p.N + GEMM_NCHUNK - 1) / GEMM_NCHUNK;
-  const int total = nkb * npass;
+  const int nchunk = (p.N + GEMM_NCHUNK - 1) / GEMM_NCHUNK;
 
   if (tid == 0) {
-    mbar_init(bar_base + 0, 1); mbar_init(bar_base + 8, 1); mbar_init(bar_base + 16, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int i = 0; i < GEMM_MAX_SLOTS; ++i) {
+      mbar_init(bar_full_a + 8 * i, GEMM_CONV_THREADS);
+      mbar_init(bar_empty_a + 8 * i, 1);
+      mbar_init(bar_full_w + 8 * i, 1);
+      mbar_init(bar_empty_w + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_acc_full + 8 * i, 1);
+      mbar_init(bar_acc_empty + 8 * i, GEMM_EPI_WARPS * 32);
+    }
+    mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), tmem_cols);
-  tc_fence_before();
+  if (warp == 13) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
+  {   // epilogue column vectors -> smem (absent vectors: zeros; columns >= N: zeros)
+    auto stage_vec = [&](const float* src, int k) {
+      for (int c = tid; c < 512; c += GEMM_THREADS) vecs[k * 512 + c] = (src != nullptr && c < p.N) ? __ldg(src + c) : 0.f;
+    };
+    stage_vec(p.bias, 0); stage_vec(p.ln1_g, 1); stage_vec(p.ln1_b, 2); stage_vec(p.ln2_g, 3); stage_vec(p.ln2_b, 4); stage_vec(p.dot_w, 5);
+  }
+  fence_before();
   __syncthreads();
-  tc_fence_after();
+  fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const __half* Whi = reinterpret_cast<const __half*>(p.W_hi);
-  const __half* Wlo = reinterpret_cast<const __half*>(p.W_lo);
-  const int a_f4 = tid & 15, a_r0 = tid >> 4;       // float4 column 0..15, row offset 0..15
-
-  for (int it = 0; it < total; ++it) {
-    const int pass = it / nkb, kb = it - pass * nkb;
-    const int s = it & 1;
-    const int n0 = pass * GEMM_NCHUNK;
-    const int nc = min(GEMM_NCHUNK, p.N - n0);
-    const uint32_t st_base = base + s * STAGE_BYTES;
-    if (it >= 2) mbar_wait(bar_base + 8 * s, ((it >> 1) - 1) & 1);   // MMAs that read this stage have retired
-
-    // W planes via cp.async (nc rows x 8 chunks x 2 planes)
-    {
-      const int nchunks = nc * 8;
-      for (int i = tid; i < 2 * nchunks; i += GEMM_THREADS) {
-        const int plane = i >= nchunks;
-        const int j = plane ? i - nchunks : i;
-        const int r = j >> 3, c = j & 7;
-        const __half* src = (plane ? Wlo : Whi) + (size_t)(n0 + r) * p.ldw + kb * GEMM_BK + c * 8;
-        cp_async16(st_base + 2 * A_PLANE_BYTES + plane * W_PLANE_BYTES + sw128_off(r, c), src);
-      }
+  if (warp < GEMM_EPI_WARPS) {
+    // ------------------------------------------------------------------------------------------ epilogue warps
+    float* st = staging + warp * (32 * TR_STRIDE);
+    const EpiVec ev = {vecs, vecs + 512, vecs + 1024, vecs + 1536, vecs + 2048, vecs + 2560};
+    int t = 0;
+    for (int tile = blockIdx.x; tile < sc.ntiles; tile += gridDim.x, ++t) {
+      const int buf = t % sc.nbuf, use = t / sc.nbuf;
+      mbar_wait(bar_acc_full + 8 * buf, (uint32_t)(use & 1));
+      fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * GEMM_NCHUNK);
+      epilogue_rows(p, ev, st, t_row, tile * GEMM_BM + warp * 32, lane);
+      fence_before();
+      mbar_arrive(bar_acc_empty + 8 * buf);
     }
-    // A: fp32 -> (hi, lo) fp16
-    {
-      float4 v[8];
+  } else if (warp < GEMM_EPI_WARPS + GEMM_CONV_WARPS) {
+    // ------------------------------------------------------------------------------------------ A converters
+    const int ct = tid - GEMM_EPI_WARPS * 32;
+    const int a_f4 = ct & 15, a_r0 = ct >> 4;       // float4 column 0..15, row offset 0..15
+    const int my_tiles = (sc.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int items = my_tiles * nkb;
+    float4 cur[8], nxt[8];
+    auto load_item = [&](int item, float4* v) {
+      const int tl = item / nkb, kb = item - tl * nkb;
+      const int m0 = ((int)blockIdx.x + tl * (int)gridDim.x) * GEMM_BM;
       const int kcol = kb * GEMM_BK + a_f4 * 4;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int r = a_r0 + 16 * i;
-        const int gm = m0 + r;
+        const int gm = m0 + a_r0 + 16 * i;
         v[i] = (gm < p.M && kcol < p.K) ? ldg4(p.A + (size_t)gm * p.lda + kcol) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if (items > 0) load_item(0, cur);
+    for (int item = 0; item < items; ++item) {
+      if (item + 1 < items) load_item(item + 1, nxt);
+      const int slot = item % sc.na, use = item / sc.na;
+      mbar_wait(bar_empty_a + 8 * slot, (uint32_t)((use & 1) ^ 1));
+      uint8_t* dst = base_ptr + slot * A_SLOT_BYTES;
+      if (p.a_scale != 1.0f) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { cur[i].x *= p.a_scale; cur[i].y *= p.a_scale; cur[i].z *= p.a_scale; cur[i].w *= p.a_scale; }
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = a_r0 + 16 * i;
         uint2 hi, lo;
-        split4(v[i], p.a_scale, hi, lo);
-        const uint32_t off = sw128_off(r, a_f4 >> 1) + (a_f4 & 1) * 8;
-        *reinterpret_cast<uint2*>(base_ptr + s * STAGE_BYTES + off) = hi;
-        *reinterpret_cast<uint2*>(base_ptr + s * STAGE_BYTES + A_PLANE_BYTES + off) = lo;
+        split4(cur[i], hi, lo);
+        const uint32_t off = sw128_off(r, a_f4 >> 1) + (uint32_t)(a_f4 & 1) * 8;
+        *reinterpret_cast<uint2*>(dst + off) = hi;
+        *reinterpret_cast<uint2*>(dst + A_PLANE_BYTES + off) = lo;
       }
+      fence_async_smem();
+      mbar_arrive(bar_full_a + 8 * slot);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
     }
-    cp_async_wait_all();
-    fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(nc >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
-      const uint32_t d_tmem = tmem_base + (uint32_t)n0;
-      const uint32_t a_hi = st_base, a_lo = st_base + A_PLANE_BYTES;
-      const uint32_t w_hi = st_base + 2 * A_PLANE_BYTES, w_lo = w_hi + W_PLANE_BYTES;
-#pragma unroll
-      for (int ks = 0; ks < GEMM_BK / 16; ++ks) {
-        const uint32_t ko = ks * 32;
-        umma_f16(d_tmem, make_desc_sw128(a_lo + ko), make_desc_sw128(w_hi + ko), idesc, (kb | ks) != 0);
-        umma_f16(d_tmem, make_desc_sw128(a_hi + ko), make_desc_sw128(w_lo + ko), idesc, 1);
-        umma_f16(d_tmem, make_desc_sw128(a_hi + ko), make_desc_sw128(w_hi + ko), idesc, 1);
-      }
-      umma_commit(bar_base + 8 * s);
-      if (it == total - 1) umma_commit(bar_base + 16);
-    }
-  }
-  mbar_wait(bar_base + 16, 0);
-  tc_fence_after();
-  __syncthreads();   // every MMA retired: pipeline smem is free for the epilogue staging tiles
-
-  // ------------------------------------------------------------------ epilogue: warps 0..3, thread = row
-  if (warp < 4) {
-    float* st = reinterpret_cast<float*>(base_ptr) + warp * (32 * TR_STRIDE);
-    const int row0 = m0 + warp * 32;
-    const int row = row0 + lane;
-    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const float inv_scale = 1.0f / p.a_scale;
-    const bool has_ln1 = p.ln1_g != nullptr, has_ln2 = p.ln2_g != nullptr;
-    const bool writeback = has_ln1 || has_ln2;
-    const float invN = 1.0f / (float)p.N;
-    const int rbi = (p.row_bias_index != nullptr && row < p.M) ? p.row_bias_index[row] : 0;
-    float v[32], t[32];
-    float sum = 0.f, dot = 0.f;
-
-    auto finish = [&](int c0) {   // v holds the post-LN values of columns [c0, c0+32)
-      apply_act_chunk<32>(v, p.act_post);
-      if (p.r_post != nullptr) {
-        warp_load_tile(st, t, p.r_post, p.ld_r_post, row0, c0, p.M, p.N, lane);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += t[j];
-      }
-      if (p.dot_w != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) if (c0 + j < p.N) dot = fmaf(v[j], __ldg(p.dot_w + c0 + j), dot);
-      }
-      if (p.C != nullptr) warp_store_tile(st, v, p.C, p.ldc, row0, c0, p.M, p.N, lane);
-    };
-
-    // pass 1: v = acc/scale + bias (+row_bias) (+r_pre); act_pre
-    for (int c0 = 0; c0 < p.N; c0 += 32) {
-      tmem_ld32(t_row + (uint32_t)c0, v);
-      if (p.r_pre != nullptr) warp_load_tile(st, t, p.r_pre, p.ld_r_pre, row0, c0, p.M, p.N, lane);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int c = c0 + j;
-        float x = v[j] * inv_scale;
-        if (c < p.N) {
-          if (p.bias != nullptr) x += __ldg(p.bias + c);
-          if (p.row_bias != nullptr) x += __ldg(p.row_bias + (size_t)rbi * p.ld_row_bias + c);
-          if (p.r_pre != nullptr) x += t[j];
-        } else x = 0.f;
-        v[j] = x;
-      }
-      if (p.act_pre != DGDM_ACT_NONE) {
-        apply_act_chunk<32>(v, p.act_pre);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) if (c0 + j >= p.N) v[j] = 0.f;
-      }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) sum += v[j];
-      if (writeback) tmem_st32(t_row + (uint32_t)c0, v);
-      else finish(c0);
-    }
-    if (writeback) {
-      const float* g = has_ln1 ? p.ln1_g : p.ln2_g;
-      const float* b = has_ln1 ? p.ln1_b : p.ln2_b;
-      float mean = sum * invN, ss = 0.f;
-      for (int c0 = 0; c0 < p.N; c0 += 32) {
-        tmem_ld32(t_row + (uint32_t)c0, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) if (c0 + j < p.N) { float d = v[j] - mean; ss = fmaf(d, d, ss); }
-      }
-      float rstd = rsqrtf(ss * invN + p.ln_eps);
-      if (has_ln1 && has_ln2) {
-        float sum2 = 0.f;
-        for (int c0 = 0; c0 < p.N; c0 += 32) {
-          tmem_ld32(t_row + (uint32_t)c0, v);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = c0 + j;
-            float y = (c < p.N) ? (v[j] - mean) * rstd * __ldg(g + c) + __ldg(b + c) : 0.f;
-            v[j] = y; sum2 += y;
+  } else if (warp == 12) {
+    // ------------------------------------------------------------------------------------------ W producer
+    if (elect_one()) {
+      const uint8_t* Wimg = reinterpret_cast<const uint8_t*>(p.W_hi);
+      int unit = 0;
+      for (int tile = blockIdx.x; tile < sc.ntiles; tile += gridDim.x) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          for (int ch = 0; ch < nchunk; ++ch, ++unit) {
+            const int n0 = ch * GEMM_NCHUNK;
+            const int nc = min(GEMM_NCHUNK, p.N - n0);
+            const int slot = unit % sc.nw, use = unit / sc.nw;
+            mbar_wait(bar_empty_w + 8 * slot, (uint32_t)((use & 1) ^ 1));
+            const uint32_t bytes = (uint32_t)nc * 128u;
+            const uint32_t dst = w_ring + (uint32_t)slot * (uint32_t)sc.w_slot_bytes;
+            const uint8_t* src = Wimg + (size_t)kb * 2 * (size_t)sc.w_plane_stride + (size_t)n0 * 128;
+            mbar_arrive_expect_tx(bar_full_w + 8 * slot, 2 * bytes);
+            bulk_g2s(dst, src, bytes, bar_full_w + 8 * slot);
+            bulk_g2s(dst + (uint32_t)(sc.w_slot_bytes >> 1), src + sc.w_plane_stride, bytes, bar_full_w + 8 * slot);
           }
-          tmem_st32(t_row + (uint32_t)c0, v);
         }
-        mean = sum2 * invN; ss = 0.f;
-        for (int c0 = 0; c0 < p.N; c0 += 32) {
-          tmem_ld32(t_row + (uint32_t)c0, v);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (c0 + j < p.N) { float d = v[j] - mean; ss = fmaf(d, d, ss); }
-        }
-        rstd = rsqrtf(ss * invN + p.ln_eps);
-        g = p.ln2_g; b = p.ln2_b;
-      }
-      for (int c0 = 0; c0 < p.N; c0 += 32) {
-        tmem_ld32(t_row + (uint32_t)c0, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int c = c0 + j;
-          v[j] = (c < p.N) ? (v[j] - mean) * rstd * __ldg(g + c) + __ldg(b + c) : 0.f;
-        }
-        finish(c0);
       }
     }
-    if (p.dot_out != nullptr && row < p.M) p.dot_out[row] = apply_act(dot + p.dot_b, p.dot_act);
+  } else {
+    // ------------------------------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      int item = 0, unit = 0, t = 0;
+      for (int tile = blockIdx.x; tile < sc.ntiles; tile += gridDim.x, ++t) {
+        const int buf = t % sc.nbuf, ause = t / sc.nbuf;
+        mbar_wait(bar_acc_empty + 8 * buf, (uint32_t)((ause & 1) ^ 1));
+        fence_after();
+        for (int kb = 0; kb < nkb; ++kb, ++item) {
+          const int sa = item % sc.na;
+          mbar_wait(bar_full_a + 8 * sa, (uint32_t)((item / sc.na) & 1));
+          const uint32_t a_hi = a_ring + (uint32_t)sa * A_SLOT_BYTES, a_lo = a_hi + A_PLANE_BYTES;
+          for (int ch = 0; ch < nchunk; ++ch, ++unit) {
+            const int n0 = ch * GEMM_NCHUNK;
+            const int nc = min(GEMM_NCHUNK, p.N - n0);
+            const int sw = unit % sc.nw;
+            mbar_wait(bar_full_w + 8 * sw, (uint32_t)((unit / sc.nw) & 1));
+            fence_after();
+            const uint32_t w_hi = w_ring + (uint32_t)sw * (uint32_t)sc.w_slot_bytes, w_lo = w_hi + (uint32_t)(sc.w_slot_bytes >> 1);
+            const uint32_t idesc = idesc_f16(GEMM_BM, nc);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * GEMM_NCHUNK + n0);
+#pragma unroll
+            for (int ks = 0; ks < GEMM_BK / 16; ++ks) {
+              const uint32_t ko = ks * 32;
+              mma_ss(d_tmem, desc_sw128(a_lo + ko), desc_sw128(w_hi + ko), idesc, (kb | ks) != 0);
+              mma_ss(d_tmem, desc_sw128(a_hi + ko), desc_sw128(w_lo + ko), idesc, 1);
+              mma_ss(d_tmem, desc_sw128(a_hi + ko), desc_sw128(w_hi + ko), idesc, 1);
+            }
+            mma_commit(bar_empty_w + 8 * sw);
+          }
+          mma_commit(bar_empty_a + 8 * sa);
+        }
+        mma_commit(bar_acc_full + 8 * buf);
+      }
+    }
   }
-  tc_fence_before();
+  fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+  if (warp == 13) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
 }
 
-// fp32 W[N,K] -> fp16 hi/lo planes [N,Kpad]
-__global__ void split_weight_kernel(const float* __restrict__ W, int N, int K, __half* __restrict__ hi,
-                                    __half* __restrict__ lo, int Kpad) {
-  const size_t total = (size_t)N * Kpad;
+// fp32 W[N,K] -> pre-swizzled fp16 K-block images: img[kb][plane][N rows x 128 B] (SWIZZLE_128B canonical, K-major),
+// element (n, k = kb*64 + c*8 + e) of plane pl at  ((kb*2 + pl)*N)*128 + sw128_off(n, c) + e*2.  K is zero padded to Kpad.
+__global__ void split_weight_kernel(const float* __restrict__ W, int N, int K, uint8_t* __restrict__ img, int Kpad) {
+  const size_t total = (size_t)N * (Kpad / 8);                 // one thread per 16-byte chunk (8 elements)
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int n = (int)(i / Kpad), k = (int)(i - (size_t)n * Kpad);
-    float w = (k < K) ? W[(size_t)n * K + k] : 0.f;
-    __half h = __float2half_rn(w);
-    hi[i] = h;
-    lo[i] = __float2half_rn(w - __half2float(h));
+    const int n = (int)(i / (Kpad / 8)), kc = (int)(i - (size_t)n * (Kpad / 8));
+    const int kb = kc >> 3, c = kc & 7;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k0 = kc * 8 + 2 * e;
+      const float w0 = (k0 < K) ? W[(size_t)n * K + k0] : 0.f;
+      const float w1 = (k0 + 1 < K) ? W[(size_t)n * K + k0 + 1] : 0.f;
+      const __half h0 = __float2half_rn(w0), h1 = __float2half_rn(w1);
+      hi[e] = pack_half2(h0, h1);
+      lo[e] = pack_half2(__float2half_rn(w0 - __half2float(h0)), __float2half_rn(w1 - __half2float(h1)));
+    }
+    const size_t off = ((size_t)kb * 2 * N) * 128 + sw128_off(n, c);
+    *reinterpret_cast<uint4*>(img + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(img + off + (size_t)N * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
+}
+
+static int g_num_sms = 0;
+
+static int launch_gemm(const dgdm_gemm_params& p, long long plane_stride, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_f16x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM) != cudaSuccess)
+      return DGDM_ERR_LAUNCH;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_num_sms <= 0) g_num_sms = 148;
+    attr_set = true;
+  }
+  GemmSched sc;
+  const int ch_rows = p.N < GEMM_NCHUNK ? p.N : GEMM_NCHUNK;
+  sc.w_slot_bytes = 2 * ch_rows * 128;
+  if (sc.w_slot_bytes > 32768) { sc.na = 2; sc.nw = 2; }          // 64 + 128 KB
+  else if (sc.w_slot_bytes > 16384) { sc.na = 3; sc.nw = 3; }     // 96 + 96 KB
+  else { sc.na = 4; sc.nw = 4; }                                  // 128 + <= 64 KB
+  sc.nbuf = p.N <= GEMM_NCHUNK ? 2 : 1;
+  sc.ntiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+  sc.w_plane_stride = plane_stride;
+  const int grid = sc.ntiles < g_num_sms ? sc.ntiles : g_num_sms;
+  gemm_f16x2_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(p, sc);
+  DGDM_CHECK_LAUNCH();
+  return DGDM_OK;
 }
 
 }  // namespace dgdm
@@ -369,33 +454,43 @@ using namespace dgdm;
 
 extern "C" int dgdm_gemm_f16x2(const dgdm_gemm_params* p, void* stream) {
   if (!p || !p->A || !p->W_hi || !p->W_lo) return DGDM_ERR_INVALID;
-  if (p->N < 16 || p->N > 512 || (p->N % 16) != 0) return DGDM_ERR_INVALID;
+  if (p->N < 16 || (p->N % 16) != 0) return DGDM_ERR_INVALID;
   if (p->K < 4 || (p->K % 4) != 0 || (p->lda % 4) != 0 || (p->ldw % 64) != 0 || p->ldw < p->K) return DGDM_ERR_INVALID;
+  if ((const uint8_t*)p->W_lo != (const uint8_t*)p->W_hi + (size_t)p->N * 128) return DGDM_ERR_INVALID;   // image layout of dgdm_split_weight_f16
   if (p->M <= 0) return DGDM_OK;
   if (p->C && (p->ldc % 4) != 0) return DGDM_ERR_INVALID;
   if (p->r_pre && (p->ld_r_pre % 4) != 0) return DGDM_ERR_INVALID;
   if (p->r_post && (p->ld_r_post % 4) != 0) return DGDM_ERR_INVALID;
   if ((p->ln1_g == nullptr) != (p->ln1_b == nullptr) || (p->ln2_g == nullptr) != (p->ln2_b == nullptr)) return DGDM_ERR_INVALID;
   if (!(p->a_scale > 0.f)) return DGDM_ERR_INVALID;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_f16x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM) != cudaSuccess)
-      return DGDM_ERR_LAUNCH;
-    attr_set = true;
+  const long long plane_stride = (long long)p->N * 128;
+  if (p->N <= 512) return launch_gemm(*p, plane_stride, (cudaStream_t)stream);
+  // Rows wider than TMEM (DGDM-Large 768-d layers): raw products in column groups of <= 512, then the stand-alone
+  // row-wise epilogue over the full width.
+  if (!p->C) return DGDM_ERR_INVALID;
+  for (int g0 = 0; g0 < p->N; g0 += 512) {
+    dgdm_gemm_params raw = {};
+    raw.A = p->A; raw.lda = p->lda; raw.M = p->M; raw.K = p->K;
+    raw.W_hi = (const uint8_t*)p->W_hi + (size_t)g0 * 128;
+    raw.W_lo = (const uint8_t*)p->W_lo + (size_t)g0 * 128;
+    raw.ldw = p->ldw;
+    raw.N = (p->N - g0) < 512 ? (p->N - g0) : 512;
+    raw.C = p->C + g0; raw.ldc = p->ldc;
+    raw.a_scale = p->a_scale; raw.ln_eps = p->ln_eps;
+    const int rc = launch_gemm(raw, plane_stride, (cudaStream_t)stream);
+    if (rc != DGDM_OK) return rc;
   }
-  uint32_t cols = 32;
-  while ((int)cols < p->N) cols <<= 1;
-  const int grid = (p->M + GEMM_BM - 1) / GEMM_BM;
-  gemm_f16x2_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(*p, cols);
-  DGDM_CHECK_LAUNCH();
-  return DGDM_OK;
+  dgdm_gemm_params ep = *p;
+  ep.a_scale = 1.0f;        // the raw pass already divided the accumulators by a_scale
+  return dgdm_rowwise_epilogue(p->C, p->ldc, p->M, p->N, &ep, stream);
 }
 
 extern "C" int dgdm_split_weight_f16(const float* W, int N, int K, void* W_hi, void* W_lo, int Kpad, void* stream) {
-  if (!W || !W_hi || !W_lo || N <= 0 || K <= 0 || Kpad < K || (Kpad % 64) != 0) return DGDM_ERR_INVALID;
-  const size_t total = (size_t)N * Kpad;
+  if (!W || !W_hi || !W_lo || N <= 0 || (N % 8) != 0 || K <= 0 || Kpad < K || (Kpad % 64) != 0) return DGDM_ERR_INVALID;
+  if ((uint8_t*)W_lo != (uint8_t*)W_hi + (size_t)N * 128) return DGDM_ERR_INVALID;
+  const size_t total = (size_t)N * (Kpad / 8);
   const int blocks = (int)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
-  split_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, N, K, (__half*)W_hi, (__half*)W_lo, Kpad);
+  split_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, N, K, (uint8_t*)W_hi, Kpad);
   DGDM_CHECK_LAUNCH();
   return DGDM_OK;
 }

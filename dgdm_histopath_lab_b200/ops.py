@@ -89,18 +89,26 @@ def device_check(dev=0):
 
 # ------------------------------------------------------------------------------------------------ weights
 class SplitWeight:
-    """fp16 hi/lo planes [N, Kpad] of an fp32 [N, K] weight + the fp32 original (for the SIMT comparator)."""
-    __slots__ = ("hi", "lo", "N", "K", "Kpad", "w32")
+    """fp16 hi/lo planes of an fp32 [N, K] weight as pre-swizzled K-block images (dgdm_split_weight_f16:
+    img[kb][plane][N rows x 128 B], SWIZZLE_128B canonical layout) + the fp32 original (for the SIMT comparator)."""
+    __slots__ = ("img", "N", "K", "Kpad", "w32")
 
     def __init__(self, w):
         w = _f32c(w.detach()).contiguous()
         self.N, self.K = w.shape
         self.Kpad = (self.K + 63) // 64 * 64
-        self.hi = torch.empty(self.N, self.Kpad, dtype=torch.float16, device=w.device)
-        self.lo = torch.empty_like(self.hi)
+        self.img = torch.empty(self.N * self.Kpad * 4, dtype=torch.uint8, device=w.device)
         self.w32 = w
-        _check(_lib.load().dgdm_split_weight_f16(_p(w), self.N, self.K, _p(self.hi), _p(self.lo), self.Kpad, _stream()),
+        _check(_lib.load().dgdm_split_weight_f16(_p(w), self.N, self.K, self.hi_ptr, self.lo_ptr, self.Kpad, _stream()),
                "dgdm_split_weight_f16")
+
+    @property
+    def hi_ptr(self):
+        return C.c_void_p(self.img.data_ptr())
+
+    @property
+    def lo_ptr(self):
+        return C.c_void_p(self.img.data_ptr() + self.N * 128)
 
 
 def gemm_mode():
@@ -122,7 +130,7 @@ def linear(a, w, bias=None, *, r_pre=None, act_pre=None, ln1=None, ln2=None, act
     N = w.N
     p = GemmParams()
     p.A, p.lda, p.M, p.K = _p(_f32c(a)), a.stride(0), M, K
-    p.W_hi, p.W_lo, p.ldw, p.N = _p(w.hi), _p(w.lo), w.Kpad, N
+    p.W_hi, p.W_lo, p.ldw, p.N = w.hi_ptr, w.lo_ptr, w.Kpad, N
     if want_out or mode == "simt" or N > 512:
         if out is None:
             out = torch.empty(M, N, dtype=torch.float32, device=a.device)
@@ -158,29 +166,12 @@ def linear(a, w, bias=None, *, r_pre=None, act_pre=None, ln1=None, ln2=None, act
     if M > 0:
         if mode == "simt":
             _check(lib.dgdm_gemm_simt(C.byref(p), _p(w.w32), _stream()), "dgdm_gemm_simt")
-        elif N > 512 or N % 16 != 0:
-            # rows wider than TMEM (DGDM-Large 768-d) or odd widths: N-chunked tensor-core product + stand-alone epilogue
-            _wide_linear(lib, p, a, w, out)
         else:
+            if N % 16 != 0:
+                raise KernelError(f"linear: output width {N} must be a multiple of 16")
+            # N > 512 (DGDM-Large 768-d rows do not fit TMEM): the C side runs column groups + the stand-alone epilogue
             _check(lib.dgdm_gemm_f16x2(C.byref(p), _stream()), "dgdm_gemm_f16x2")
     return (out, dot_out) if dot is not None else out
-
-
-def _wide_linear(lib, p, a, w, out):
-    M, N = out.shape
-    if N % 16 != 0:
-        raise KernelError(f"linear: output width {N} must be a multiple of 16")
-    raw = GemmParams()
-    for n0 in range(0, N, 512):
-        nc = min(512, N - n0)
-        raw.A, raw.lda, raw.M, raw.K = p.A, p.lda, p.M, p.K
-        raw.W_hi = C.c_void_p(w.hi.data_ptr() + n0 * w.Kpad * 2)
-        raw.W_lo = C.c_void_p(w.lo.data_ptr() + n0 * w.Kpad * 2)
-        raw.ldw, raw.N = w.Kpad, nc
-        raw.C, raw.ldc = C.c_void_p(out.data_ptr() + n0 * 4), out.stride(0)
-        raw.a_scale, raw.ln_eps = p.a_scale, p.ln_eps
-        _check(lib.dgdm_gemm_f16x2(C.byref(raw), _stream()), "dgdm_gemm_f16x2")
-    _check(lib.dgdm_rowwise_epilogue(_p(out), out.stride(0), M, N, C.byref(p), _stream()), "dgdm_rowwise_epilogue")
 
 
 # ------------------------------------------------------------------------------------------------ graph

@@ -40,15 +40,18 @@ int dgdm_device_check(int dev);
  * row-wise epilogue that follows them in the reference fused in:
  *     v = A @ W^T (+bias) (+r_pre) ; v = act_pre(v) ; [v = LN1(v)] ; [v = LN2(v)] ; v = act_post(v) (+r_post)
  *     C = v ;  optionally dot_out[m] = dot_act(sum_n v[m,n]*dot_w[n] + dot_b)
- * W is supplied pre-split into two fp16 planes (hi = fp16(w), lo = fp16(w - hi)), [N, Kpad] row-major with
- * Kpad = round_up(K, 64) zero padded (dgdm_split_weight_f16 makes them).  A is fp32 and is split the same way
- * inside the kernel; the product is hi*hi + lo*hi + hi*lo on tcgen05 (kind::f16, fp32 accumulate in TMEM),
- * ~2^-21 relative — fp32-class, not TF32-class.
- * Limits: N % 16 == 0, 16 <= N <= 512, K % 4 == 0, lda % 4 == 0, pointers 16-byte aligned.
+ * W is supplied pre-split into two fp16 planes (hi = fp16(w), lo = fp16(w - hi)) stored as pre-swizzled K-block images
+ * made by dgdm_split_weight_f16: img[kb][plane][N rows x 128 B] with Kpad = round_up(K, 64) zero padded, every
+ * [N x 64] tile already in the tcgen05 K-major SWIZZLE_128B canonical layout so that one cp.async.bulk lands it in
+ * shared memory. W_hi = image base, W_lo = W_hi + N*128 (the lo plane of K-block 0), ldw = Kpad; the buffer holds
+ * N*Kpad*4 bytes. A is fp32 and is split the same way inside the kernel; the product is hi*hi + lo*hi + hi*lo on
+ * tcgen05 (kind::f16, fp32 accumulate in TMEM), ~2^-21 relative — fp32-class, not TF32-class.
+ * Limits: N % 16 == 0, N >= 16 (N > 512 runs as column groups of 512 + dgdm_rowwise_epilogue and needs C),
+ * K % 4 == 0, lda % 4 == 0, pointers 16-byte aligned.
  */
 typedef struct {
   const float* A; int lda; int M; int K;
-  const void* W_hi; const void* W_lo; int ldw;   /* fp16 [N, ldw], ldw = Kpad */
+  const void* W_hi; const void* W_lo; int ldw;   /* pre-swizzled images (see above), ldw = Kpad */
   int N;
   float* C; int ldc;                              /* may be NULL when only dot_out is wanted */
   const float* bias;                              /* [N] or NULL */
@@ -68,7 +71,7 @@ typedef struct {
 int dgdm_gemm_f16x2(const dgdm_gemm_params* p, void* stream);
 /* Plain fp32 SIMT GEMM with the same epilogue: bring-up / on-device comparator only. W32 is fp32 [N,K]. */
 int dgdm_gemm_simt(const dgdm_gemm_params* p, const float* W32, void* stream);
-/* Split fp32 W[N,K] into fp16 hi/lo planes [N,Kpad] (zero padded). */
+/* Split fp32 W[N,K] (N % 8 == 0) into the fp16 hi/lo K-block images described above; W_lo must be W_hi + N*128. */
 int dgdm_split_weight_f16(const float* W, int N, int K, void* W_hi, void* W_lo, int Kpad, void* stream);
 
 /* Stand-alone row-wise epilogue for widths that do not fit TMEM (N > 512, DGDM-Large 768-d layers):

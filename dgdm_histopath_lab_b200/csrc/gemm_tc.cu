@@ -39,6 +39,14 @@ constexpr int GEMM_MAX_SLOTS = 4;
 constexpr int GEMM_VEC_BYTES = 6 * 512 * 4;                                    // bias, ln1 g/b, ln2 g/b, dot_w
 constexpr int GEMM_SMEM = GEMM_RING_BYTES + GEMM_STAGING_BYTES + GEMM_VEC_BYTES + 256 /*barriers*/ + 1024 /*align*/;
 
+#ifdef DGDM_GEMM_TRACE
+// dev-only instrumentation (tools/gemm_trace.sh): cycles each role spends in its waits, per CTA
+__device__ long long g_gemm_events[12][64];      // CTA 0 event times (cycles since the thread entered the kernel)
+#define TRACE_EVENT(role, idx) do { if (blockIdx.x == 0 && (idx) < 64) g_gemm_events[role][idx] = clock64() - t_kernel0; } while (0)
+#else
+#define TRACE_EVENT(role, idx)
+#endif
+
 struct GemmSched {
   int na, nw;              // ring depths
   int w_slot_bytes;        // bytes per W ring slot (2 planes x chunk rows x 128 B)
@@ -107,7 +115,6 @@ __device__ __forceinline__ void warp_load_tile(float* st, float* v, const float*
 // Column vectors of the epilogue staged once per CTA in shared memory (zero / one filled when absent) so that the element
 // loops below are branch-free FFMA chains fed by broadcast LDS.128 instead of per-element predicated global loads.
 struct EpiVec { const float* bias; const float* g1; const float* b1; const float* g2; const float* b2; const float* dotw; };
-constexpr int EPI_VEC_FLOATS = 6 * 512;
 
 __device__ __forceinline__ void lds_row32(const float* s, float* o) {
 #pragma unroll
@@ -252,6 +259,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16x2_kernel(const dgdm_
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + GEMM_RING_BYTES + GEMM_STAGING_BYTES + GEMM_VEC_BYTES + 192);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef DGDM_GEMM_TRACE
+  const long long t_kernel0 = clock64();
+#endif
   const int nkb = (p.K + GEMM_BK - 1) / GEMM_BK;
   const int nchunk = (p.N + GEMM_NCHUNK - 1) / GEMM_NCHUNK;
 
@@ -264,7 +274,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16x2_kernel(const dgdm_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_acc_full + 8 * i, 1);
-      mbar_init(bar_acc_empty + 8 * i, GEMM_EPI_WARPS * 32);
+      mbar_init(bar_acc_empty + 8 * i, GEMM_EPI_WARPS);
     }
     mbar_fence_init();
   }
@@ -279,6 +289,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16x2_kernel(const dgdm_
   __syncthreads();
   fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) TRACE_EVENT(11, 0);
 
   if (warp < GEMM_EPI_WARPS) {
     // ------------------------------------------------------------------------------------------ epilogue warps
@@ -287,12 +298,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16x2_kernel(const dgdm_
     int t = 0;
     for (int tile = blockIdx.x; tile < sc.ntiles; tile += gridDim.x, ++t) {
       const int buf = t % sc.nbuf, use = t / sc.nbuf;
-      mbar_wait(bar_acc_full + 8 * buf, (uint32_t)(use & 1));
+      mbar_wait_warp(bar_acc_full + 8 * buf, (uint32_t)(use & 1), lane);
       fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * GEMM_NCHUNK);
+      if (tid == 0) TRACE_EVENT(2, t);
       epilogue_rows(p, ev, st, t_row, tile * GEMM_BM + warp * 32, lane);
+      if (tid == 0) TRACE_EVENT(3, t);
       fence_before();
-      mbar_arrive(bar_acc_empty + 8 * buf);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
     }
   } else if (warp < GEMM_EPI_WARPS + GEMM_CONV_WARPS) {
     // ------------------------------------------------------------------------------------------ A converters
@@ -300,40 +314,57 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16x2_kernel(const dgdm_
     const int a_f4 = ct & 15, a_r0 = ct >> 4;       // float4 column 0..15, row offset 0..15
     const int my_tiles = (sc.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int items = my_tiles * nkb;
-    float4 cur[8], nxt[8];
-    auto load_item = [&](int item, float4* v) {
+    // Rolling two-item register window: while item i is converted row by row, each freed register is refilled at once
+    // with the same row of item i+2, so ~12-16 float4 (up to 64 KB per SM) of global loads stay in flight.
+    float4 b0[8], b1[8];
+    struct ItemAddr { const float* ptr; int rows_left; bool kok; };
+    auto item_addr = [&](int item) {
+      ItemAddr ia;
       const int tl = item / nkb, kb = item - tl * nkb;
-      const int m0 = ((int)blockIdx.x + tl * (int)gridDim.x) * GEMM_BM;
+      const int m0 = ((int)blockIdx.x + tl * (int)gridDim.x) * GEMM_BM + a_r0;
       const int kcol = kb * GEMM_BK + a_f4 * 4;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int gm = m0 + a_r0 + 16 * i;
-        v[i] = (gm < p.M && kcol < p.K) ? ldg4(p.A + (size_t)gm * p.lda + kcol) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      ia.ptr = p.A + (size_t)m0 * p.lda + kcol;
+      ia.rows_left = p.M - m0;                   // row i of the item is valid iff 16*i < rows_left
+      ia.kok = item < items && kcol < p.K;
+      return ia;
     };
-    if (items > 0) load_item(0, cur);
-    for (int item = 0; item < items; ++item) {
-      if (item + 1 < items) load_item(item + 1, nxt);
+    auto load_row = [&](const ItemAddr& ia, int i) {
+      return (ia.kok && 16 * i < ia.rows_left) ? ldg4(ia.ptr + (size_t)(16 * i) * p.lda) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto process = [&](int item, float4* buf) {
+      const ItemAddr nx = item_addr(item + 2);
       const int slot = item % sc.na, use = item / sc.na;
-      mbar_wait(bar_empty_a + 8 * slot, (uint32_t)((use & 1) ^ 1));
+      mbar_wait_poll(bar_empty_a + 8 * slot, (uint32_t)((use & 1) ^ 1));
+      if (ct == 0) TRACE_EVENT(4, item);
       uint8_t* dst = base_ptr + slot * A_SLOT_BYTES;
-      if (p.a_scale != 1.0f) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { cur[i].x *= p.a_scale; cur[i].y *= p.a_scale; cur[i].z *= p.a_scale; cur[i].w *= p.a_scale; }
-      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = a_r0 + 16 * i;
+        float4 x = buf[i];
+        if (p.a_scale != 1.0f) { x.x *= p.a_scale; x.y *= p.a_scale; x.z *= p.a_scale; x.w *= p.a_scale; }
         uint2 hi, lo;
-        split4(cur[i], hi, lo);
+        split4(x, hi, lo);
         const uint32_t off = sw128_off(r, a_f4 >> 1) + (uint32_t)(a_f4 & 1) * 8;
         *reinterpret_cast<uint2*>(dst + off) = hi;
         *reinterpret_cast<uint2*>(dst + A_PLANE_BYTES + off) = lo;
+        buf[i] = load_row(nx, i);
       }
+      if (ct == 0) TRACE_EVENT(5, item);
       fence_async_smem();
-      mbar_arrive(bar_full_a + 8 * slot);
+      if (ct == 0) TRACE_EVENT(6, item);
+      mbar_arrive(bar_full_a + 8 * slot);      // per-thread arrive: a warp-elected arrive behind __syncwarp measured 2x slower
+      if (ct == 0) TRACE_EVENT(0, item);
+    };
+    {
+      const ItemAddr i0 = item_addr(0), i1 = item_addr(1);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+      for (int i = 0; i < 8; ++i) b0[i] = load_row(i0, i);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) b1[i] = load_row(i1, i);
+    }
+    for (int item = 0; item < items; item += 2) {
+      process(item, b0);
+      if (item + 1 < items) process(item + 1, b1);
     }
   } else if (warp == 12) {
     // ------------------------------------------------------------------------------------------ W producer
@@ -346,7 +377,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16x2_kernel(const dgdm_
             const int n0 = ch * GEMM_NCHUNK;
             const int nc = min(GEMM_NCHUNK, p.N - n0);
             const int slot = unit % sc.nw, use = unit / sc.nw;
-            mbar_wait(bar_empty_w + 8 * slot, (uint32_t)((use & 1) ^ 1));
+            mbar_wait_poll(bar_empty_w + 8 * slot, (uint32_t)((use & 1) ^ 1));
+            TRACE_EVENT(7, unit);
             const uint32_t bytes = (uint32_t)nc * 128u;
             const uint32_t dst = w_ring + (uint32_t)slot * (uint32_t)sc.w_slot_bytes;
             const uint8_t* src = Wimg + (size_t)kb * 2 * (size_t)sc.w_plane_stride + (size_t)n0 * 128;
@@ -363,17 +395,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16x2_kernel(const dgdm_
       int item = 0, unit = 0, t = 0;
       for (int tile = blockIdx.x; tile < sc.ntiles; tile += gridDim.x, ++t) {
         const int buf = t % sc.nbuf, ause = t / sc.nbuf;
-        mbar_wait(bar_acc_empty + 8 * buf, (uint32_t)((ause & 1) ^ 1));
+        mbar_wait_poll(bar_acc_empty + 8 * buf, (uint32_t)((ause & 1) ^ 1));
         fence_after();
         for (int kb = 0; kb < nkb; ++kb, ++item) {
           const int sa = item % sc.na;
-          mbar_wait(bar_full_a + 8 * sa, (uint32_t)((item / sc.na) & 1));
+          mbar_wait_poll(bar_full_a + 8 * sa, (uint32_t)((item / sc.na) & 1));
+          TRACE_EVENT(8, item);
           const uint32_t a_hi = a_ring + (uint32_t)sa * A_SLOT_BYTES, a_lo = a_hi + A_PLANE_BYTES;
           for (int ch = 0; ch < nchunk; ++ch, ++unit) {
             const int n0 = ch * GEMM_NCHUNK;
             const int nc = min(GEMM_NCHUNK, p.N - n0);
             const int sw = unit % sc.nw;
-            mbar_wait(bar_full_w + 8 * sw, (uint32_t)((unit / sc.nw) & 1));
+            mbar_wait_poll(bar_full_w + 8 * sw, (uint32_t)((unit / sc.nw) & 1));
+            TRACE_EVENT(9, unit);
             fence_after();
             const uint32_t w_hi = w_ring + (uint32_t)sw * (uint32_t)sc.w_slot_bytes, w_lo = w_hi + (uint32_t)(sc.w_slot_bytes >> 1);
             const uint32_t idesc = idesc_f16(GEMM_BM, nc);
@@ -388,8 +422,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16x2_kernel(const dgdm_
             mma_commit(bar_empty_w + 8 * sw);
           }
           mma_commit(bar_empty_a + 8 * sa);
+          TRACE_EVENT(10, item);
         }
         mma_commit(bar_acc_full + 8 * buf);
+        TRACE_EVENT(1, t);
       }
     }
   }
@@ -451,6 +487,14 @@ static int launch_gemm(const dgdm_gemm_params& p, long long plane_stride, cudaSt
 }  // namespace dgdm
 
 using namespace dgdm;
+
+#ifdef DGDM_GEMM_TRACE
+extern "C" int dgdm_debug_gemm_trace(long long* host_out, int reset) {
+  if (host_out && cudaMemcpyFromSymbol(host_out, g_gemm_events, sizeof(long long) * 12 * 64) != cudaSuccess) return DGDM_ERR_LAUNCH;
+  if (reset) { static long long z[12 * 64]; if (cudaMemcpyToSymbol(g_gemm_events, z, sizeof(z)) != cudaSuccess) return DGDM_ERR_LAUNCH; }
+  return DGDM_OK;
+}
+#endif
 
 extern "C" int dgdm_gemm_f16x2(const dgdm_gemm_params* p, void* stream) {
   if (!p || !p->A || !p->W_hi || !p->W_lo) return DGDM_ERR_INVALID;

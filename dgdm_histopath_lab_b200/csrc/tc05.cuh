@@ -32,6 +32,33 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (++spins > (1u << 26)) { asm volatile("trap;"); }
   }
 }
+// Pure polling wait (mbarrier.test_wait never suspends the thread).
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_poll(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_test_wait(bar, parity)) {
+    if (++spins > (1u << 28)) { asm volatile("trap;"); }
+  }
+}
+// Warp-level wait: lane 0 polls, the other lanes are released by __syncwarp (which also orders memory among the warp's lanes).
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int lane, uint32_t backoff_ns = 0) {
+  if (lane == 0) {
+    uint32_t spins = 0;
+    while (!mbar_test_wait(bar, parity)) {
+      if (backoff_ns) __nanosleep(backoff_ns);
+      if (++spins > (1u << 28)) { asm volatile("trap;"); }
+    }
+  }
+  __syncwarp();
+}
 // try_wait with a suspend-time hint: the thread is parked by the hardware for up to `ns` instead of spinning, so a waiting
 // producer / MMA-issuer warp does not steal issue slots from the compute warps that share its scheduler.
 __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {

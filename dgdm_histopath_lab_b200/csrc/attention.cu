@@ -463,6 +463,92 @@ __global__ void pool_reduce_kernel(const float* __restrict__ partial, int D, flo
   }
 }
 
+// Fused fast path (D <= 128, head_dim % 4 == 0, head_dim/4 a power of two): one pass over k|v with an online softmax.
+// Block = (segment, chunk of the segment's rows), 8 warps; a lane owns 4 consecutive columns (LPH lanes per head), a warp owns
+// rows j0+w, j0+w+8, ... (two rows in flight). The 8 warps and then the chunks are merged in a fixed order -> deterministic.
+constexpr int POOL_FCHUNKS = 256;
+template <int LPH>
+__global__ void __launch_bounds__(256) pool_fused_kernel(const float* __restrict__ q_tok, const float* __restrict__ kv, int ld,
+                                                         const int* __restrict__ seg_ptr, int D, int heads, int chunks,
+                                                         float* __restrict__ pacc, float* __restrict__ pml) {
+  const int seg = blockIdx.x / chunks, ch = blockIdx.x - seg * chunks;
+  const int a = seg_ptr[seg], b = seg_ptr[seg + 1];
+  const int per = (b - a + chunks - 1) / chunks;
+  const int j0 = a + ch * per, j1 = min(b, j0 + per);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = lane * 4;
+  const bool on = col < D;
+  const float scale = 1.0f / sqrtf((float)(D / heads));
+  const float4 q = on ? ldg4(q_tok + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float m = -INFINITY, l = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto head_dot = [&](float4 k) {
+    float sdot = q.x * k.x + q.y * k.y + q.z * k.z + q.w * k.w;
+#pragma unroll
+    for (int o = 1; o < LPH; o <<= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
+    return sdot * scale;
+  };
+  auto update = [&](float sc, float4 v) {
+    const float mn = fmaxf(m, sc);
+    const float corr = expf(m - mn), pr = expf(sc - mn);     // m = -inf on the first row: corr = 0
+    l = l * corr + pr;
+    acc.x = acc.x * corr + pr * v.x; acc.y = acc.y * corr + pr * v.y; acc.z = acc.z * corr + pr * v.z; acc.w = acc.w * corr + pr * v.w;
+    m = mn;
+  };
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  int j = j0 + warp;
+  for (; j + 8 < j1; j += 16) {
+    const float* r0 = kv + (size_t)j * ld + col; const float* r1 = kv + (size_t)(j + 8) * ld + col;
+    const float4 k0 = on ? ldg4(r0) : z4, v0 = on ? ldg4(r0 + D) : z4, k1 = on ? ldg4(r1) : z4, v1 = on ? ldg4(r1 + D) : z4;
+    update(head_dot(k0), v0);
+    update(head_dot(k1), v1);
+  }
+  for (; j < j1; j += 8) {
+    const float* r0 = kv + (size_t)j * ld + col;
+    const float4 k0 = on ? ldg4(r0) : z4, v0 = on ? ldg4(r0 + D) : z4;
+    update(head_dot(k0), v0);
+  }
+  __shared__ float sm_m[8][32], sm_l[8][32];
+  __shared__ float4 sm_a[8][32];
+  sm_m[warp][lane] = m; sm_l[warp][lane] = l; sm_a[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && on) {
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) M = fmaxf(M, sm_m[w][lane]);
+    float L = 0.f; float4 A = z4;
+    if (M > -INFINITY) {
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const float e = expf(sm_m[w][lane] - M);
+        const float4 t = sm_a[w][lane];
+        L += sm_l[w][lane] * e; A.x += t.x * e; A.y += t.y * e; A.z += t.z * e; A.w += t.w * e;
+      }
+    }
+    *reinterpret_cast<float4*>(pacc + (size_t)blockIdx.x * D + col) = A;
+    if ((lane % LPH) == 0) { const int h = lane / LPH; pml[((size_t)blockIdx.x * heads + h) * 2] = M; pml[((size_t)blockIdx.x * heads + h) * 2 + 1] = L; }
+  }
+}
+__global__ void pool_fused_merge_kernel(const float* __restrict__ pacc, const float* __restrict__ pml, int D, int heads, int chunks,
+                                        float* __restrict__ out) {
+  const int seg = blockIdx.x;
+  const int hd = D / heads;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const int h = d / hd;
+    float M = -INFINITY;
+    for (int c = 0; c < chunks; ++c) M = fmaxf(M, pml[((size_t)(seg * chunks + c) * heads + h) * 2]);
+    float L = 0.f, A = 0.f;
+    if (M > -INFINITY)
+      for (int c = 0; c < chunks; ++c) {
+        const size_t blk = (size_t)seg * chunks + c;
+        const float e = expf(pml[(blk * heads + h) * 2] - M);
+        L += pml[(blk * heads + h) * 2 + 1] * e;
+        A += pacc[blk * D + d] * e;
+      }
+    out[(size_t)seg * D + d] = L > 0.f ? A / L : 0.f;
+  }
+}
+
 static inline int agrid(size_t n, int block = 256, int cap = 148 * 16) {
   size_t b = (n + block - 1) / block;
   return (int)(b < 1 ? 1 : (b > (size_t)cap ? cap : b));
@@ -576,13 +662,34 @@ extern "C" int dgdm_spatial_attention_weights(const float* qkv, int ld, const fl
 }
 
 extern "C" size_t dgdm_attention_pool_work_floats(int N, int D, int heads, int num_seg) {
-  return (size_t)N * heads + (size_t)2 * num_seg * heads + (size_t)num_seg * POOL_CHUNKS * D + 64;
+  const size_t generic = (size_t)N * heads + (size_t)2 * num_seg * heads + (size_t)num_seg * POOL_CHUNKS * D + 64;
+  const size_t fused = (size_t)num_seg * POOL_FCHUNKS * ((size_t)D + 2 * heads) + 64;
+  return generic > fused ? generic : fused;
 }
 
 extern "C" int dgdm_attention_pool(const float* q_tok, const float* kv, int ld_kv, const int* seg_ptr, int num_seg, int N,
                                    int D, int heads, float* out, float* work, void* stream) {
   if (!q_tok || !kv || !seg_ptr || !out || !work || num_seg <= 0 || heads <= 0 || D % heads != 0 || D > 1024) return DGDM_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
+  const int hd = D / heads, lph = hd / 4;
+  if (D <= 128 && (D % 4) == 0 && (hd % 4) == 0 && (lph & (lph - 1)) == 0 && (ld_kv % 4) == 0) {
+    int chunks = (148 * 4 + num_seg - 1) / num_seg;
+    if (chunks > POOL_FCHUNKS) chunks = POOL_FCHUNKS;
+    if (chunks < 1) chunks = 1;
+    float* pacc = work; float* pml = work + (size_t)num_seg * chunks * D;
+    const int grid = num_seg * chunks;
+    switch (lph) {
+      case 1: pool_fused_kernel<1><<<grid, 256, 0, s>>>(q_tok, kv, ld_kv, seg_ptr, D, heads, chunks, pacc, pml); break;
+      case 2: pool_fused_kernel<2><<<grid, 256, 0, s>>>(q_tok, kv, ld_kv, seg_ptr, D, heads, chunks, pacc, pml); break;
+      case 4: pool_fused_kernel<4><<<grid, 256, 0, s>>>(q_tok, kv, ld_kv, seg_ptr, D, heads, chunks, pacc, pml); break;
+      case 8: pool_fused_kernel<8><<<grid, 256, 0, s>>>(q_tok, kv, ld_kv, seg_ptr, D, heads, chunks, pacc, pml); break;
+      case 16: pool_fused_kernel<16><<<grid, 256, 0, s>>>(q_tok, kv, ld_kv, seg_ptr, D, heads, chunks, pacc, pml); break;
+      default: pool_fused_kernel<32><<<grid, 256, 0, s>>>(q_tok, kv, ld_kv, seg_ptr, D, heads, chunks, pacc, pml); break;
+    }
+    pool_fused_merge_kernel<<<num_seg, 128, 0, s>>>(pacc, pml, D, heads, chunks, out);
+    DGDM_CHECK_LAUNCH();
+    return DGDM_OK;
+  }
   float* scores = work; float* stats = scores + (size_t)N * heads; float* partial = stats + (size_t)2 * num_seg * heads;
   if (N > 0) pool_scores_kernel<<<agrid((size_t)N * heads), 256, 0, s>>>(q_tok, kv, ld_kv, N, D, heads, scores);
   pool_stats_kernel<<<num_seg * heads, 256, 0, s>>>(scores, seg_ptr, heads, stats);

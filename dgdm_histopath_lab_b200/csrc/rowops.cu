@@ -162,19 +162,27 @@ __global__ void ddpm_update_kernel(const float* __restrict__ x, const float* __r
 
 // ------------------------------------------------------------------------------------------ spatial PE
 // per-segment min/max over all coordinates of pos[seg] (core/attention.py:238-240: scalar min/max of the graph's positions)
-__global__ void __launch_bounds__(256) segment_minmax_kernel(const float* __restrict__ pos, const int* __restrict__ seg_ptr,
-                                                             float* __restrict__ minmax) {
+__global__ void __launch_bounds__(1024) segment_minmax_kernel(const float* __restrict__ pos, const int* __restrict__ seg_ptr,
+                                                              float* __restrict__ minmax) {
   const int g = blockIdx.x;
-  const int a = seg_ptr[g] * 2, b = seg_ptr[g + 1] * 2;
+  const int a = seg_ptr[g] * 2, b = seg_ptr[g + 1] * 2;       // [N,2] rows are 8-byte aligned: float2 loads, 4 in flight per thread
   float mn = INFINITY, mx = -INFINITY;
-  for (int i = a + threadIdx.x; i < b; i += blockDim.x) { float v = pos[i]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
-  __shared__ float smn[8], smx[8];
+  const float2* p2 = reinterpret_cast<const float2*>(pos);
+  const int a2 = a >> 1, b2 = b >> 1;
+  int i = a2 + threadIdx.x;
+  for (; i + 3 * 1024 < b2; i += 4 * 1024) {
+    const float2 v0 = __ldg(p2 + i), v1 = __ldg(p2 + i + 1024), v2 = __ldg(p2 + i + 2048), v3 = __ldg(p2 + i + 3072);
+    mn = fminf(fminf(fminf(mn, fminf(v0.x, v0.y)), fminf(v1.x, v1.y)), fminf(fminf(v2.x, v2.y), fminf(v3.x, v3.y)));
+    mx = fmaxf(fmaxf(fmaxf(mx, fmaxf(v0.x, v0.y)), fmaxf(v1.x, v1.y)), fmaxf(fmaxf(v2.x, v2.y), fmaxf(v3.x, v3.y)));
+  }
+  for (; i < b2; i += 1024) { const float2 v = __ldg(p2 + i); mn = fminf(mn, fminf(v.x, v.y)); mx = fmaxf(mx, fmaxf(v.x, v.y)); }
+  __shared__ float smn[32], smx[32];
   mn = warp_min(mn); mx = warp_max(mx);
   if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = 1; i < 8; ++i) { mn = fminf(mn, smn[i]); mx = fmaxf(mx, smx[i]); }
-    minmax[2 * g] = mn; minmax[2 * g + 1] = mx;
+  if (threadIdx.x < 32) {
+    mn = warp_min(smn[threadIdx.x]); mx = warp_max(smx[threadIdx.x]);
+    if (threadIdx.x == 0) { minmax[2 * g] = mn; minmax[2 * g + 1] = mx; }
   }
 }
 // out = X + PE: channel 4f+0 = sin(x*div_f), 4f+1 = cos(x*div_f), 4f+2 = sin(y*div_f), 4f+3 = cos(y*div_f),
@@ -318,7 +326,7 @@ extern "C" int dgdm_ddpm_update(const float* x, const float* eps_pred, const flo
 
 extern "C" int dgdm_segment_minmax(const float* pos, const int* seg_ptr, int num_seg, float* minmax, void* stream) {
   if (!pos || !seg_ptr || !minmax || num_seg <= 0) return DGDM_ERR_INVALID;
-  segment_minmax_kernel<<<num_seg, 256, 0, (cudaStream_t)stream>>>(pos, seg_ptr, minmax);
+  segment_minmax_kernel<<<num_seg, 1024, 0, (cudaStream_t)stream>>>(pos, seg_ptr, minmax);
   DGDM_CHECK_LAUNCH();
   return DGDM_OK;
 }

@@ -20,7 +20,7 @@ KERNELS_PER_CALL = {
     "dgdm_gemm_f16x2": 1, "dgdm_gemm_simt": 2, "dgdm_split_weight_f16": 1, "dgdm_rowwise_epilogue": 1, "dgdm_csr_build": 5,
     "dgdm_spmm_gcn": 1, "dgdm_edge_attr_aggregate": 1, "dgdm_topk_select": 10, "dgdm_pool_gather": 1, "dgdm_csr_pool": 3,
     "dgdm_unpool_add_act": 1, "dgdm_segment_softmax_scores": 1, "dgdm_segment_minmax": 1, "dgdm_spatial_pe_add": 1,
-    "dgdm_spatial_attention": 6, "dgdm_spatial_attention_weights": 1, "dgdm_attention_pool": 4, "dgdm_diffusion_add_noise": 1,
+    "dgdm_spatial_attention": 6, "dgdm_spatial_attention_weights": 1, "dgdm_attention_pool": 2, "dgdm_diffusion_add_noise": 1,
     "dgdm_groupnorm_silu": 1, "dgdm_ddpm_update": 1, "dgdm_validate_inputs": 1, "dgdm_knn_cosine": 4, "dgdm_knn2d": 2,
 }
 LAUNCHES = {"kernels": 0, "calls": 0}

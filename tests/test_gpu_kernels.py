@@ -191,6 +191,26 @@ def test_attention_pool_vs_oracle():
     assert rel_err(out, ref)[0] < 1e-5
 
 
+@pytest.mark.parametrize("D,heads", [(128, 8), (128, 16), (64, 8), (48, 4), (32, 2)])
+def test_attention_pool_shapes_and_empty_segment(D, heads):
+    """fused one-pass kernel (head_dim/4 a power of two) and the generic fallback (48/4 -> head_dim 12) vs a dense softmax"""
+    g = _gen(D + heads)
+    N = 5000
+    kv = torch.randn(N, 2 * D, generator=g); q = torch.randn(D, generator=g)
+    seg_host = [0, 1700, 1700, 5000]                                  # middle segment empty -> zeros
+    seg = torch.tensor(seg_host, dtype=torch.int32, device=DEV)
+    out = ops.attention_pool(q.to(DEV), kv.to(DEV), seg, 3, heads)
+    hd = D // heads
+    ref = torch.zeros(3, D, dtype=torch.float64)
+    for s_ in range(3):
+        a, b = seg_host[s_], seg_host[s_ + 1]
+        if b > a:
+            k = kv[a:b, :D].double().view(b - a, heads, hd); v = kv[a:b, D:].double().view(b - a, heads, hd)
+            w = torch.softmax((k * q.double().view(1, heads, hd)).sum(-1) / hd ** 0.5, dim=0)
+            ref[s_] = (w.unsqueeze(-1) * v).sum(0).reshape(D)
+    assert rel_err(out, ref)[0] < 2e-6
+
+
 def test_spatial_pe_matches_oracle():
     pos = torch.rand(200, 2, generator=_gen(4)) * 3 - 1
     x = torch.randn(200, 128, generator=_gen(5))

@@ -40,7 +40,7 @@ SIGNATURES = {
     "dgdm_rowwise_epilogue": (c_int, [c_void_p, c_int, c_int, c_int, C.POINTER(GemmParams), c_void_p]),
     "dgdm_csr_build_work_ints": (c_size_t, [c_int, c_int]),
     "dgdm_csr_build": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "dgdm_spmm_gcn": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int,
+    "dgdm_spmm_gcn": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int,
                               c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "dgdm_edge_attr_aggregate": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "dgdm_topk_pool_work_ints": (c_size_t, [c_int]),

@@ -106,18 +106,23 @@ class GraphConvolution(nn.Module):
             nn.init.zeros_(self.bias)
 
     @torch.no_grad()
-    def forward(self, x, edge_index=None, edge_attr=None, size=None, *, ctx=None, agg_attr=None, act=None, n_rows=None):
+    def forward(self, x, edge_index=None, edge_attr=None, size=None, *, ctx=None, agg_attr=None, act=None, n_rows=None, part=None):
+        """part (parallel.Part): x holds the rows this rank owns; the projected rows are all-gathered (the halo exchange) and
+        the propagate runs on the owned destination rows only. agg_attr is then the local slice as well."""
         _require_cuda(x)
         ctx = _ctx_for(x, edge_index, ctx)
         csr = ctx.csr if isinstance(ctx, GraphContext) else ctx
         h = ops.linear(x, split_weight(self.node_lin.weight))
+        rows = None
+        if part is not None:
+            h, rows, n_rows = part.gather(h), part.rows, None
         addend = None
         if self.edge_lin is not None and (edge_attr is not None or agg_attr is not None):
             if agg_attr is None:
                 agg_attr = ops.edge_attr_aggregate(csr, _pad_cols(edge_attr, self.edge_dim))
             # sum_e n_e W_e a_e = W_e (sum_e n_e a_e): one [N,32] GEMM instead of an [E+N, C] intermediate
             addend = ops.linear(agg_attr, split_weight(self.edge_lin.weight))
-        return ops.spmm_gcn(csr, h, n_rows=n_rows, addend=addend,
+        return ops.spmm_gcn(csr, h, n_rows=n_rows, rows=rows, addend=addend,
                             bias=self.bias.detach() if self.bias is not None else None, act=act)
 
 
@@ -157,15 +162,17 @@ class DynamicGraphLayer(nn.Module):
         return ops.segment_softmax_scores(ctx.csr, qkv, ek, self.hidden_dim, self.num_heads)
 
     @torch.no_grad()
-    def forward(self, x, edge_index=None, edge_attr=None, *, ctx=None, agg_attr=None, n_rows=None, post=None):
+    def forward(self, x, edge_index=None, edge_attr=None, *, ctx=None, agg_attr=None, n_rows=None, post=None, part=None):
         """post: optional dict(transition=nn.Linear|None, ln=nn.LayerNorm|None, act=str) — the encoder tail
         (models/encoders.py:267-269 + P3) fused into the output_proj epilogue where shapes allow."""
         _require_cuda(x)
         ctx = _ctx_for(x, edge_index, ctx)
         if agg_attr is None and edge_attr is not None:
             agg_attr = ops.edge_attr_aggregate(ctx.csr if isinstance(ctx, GraphContext) else ctx, _pad_cols(edge_attr, self.edge_dim))
-        h1 = self.graph_conv1(x, ctx=ctx, agg_attr=agg_attr, act="gelu", n_rows=n_rows)
-        h2 = self.graph_conv2(h1, ctx=ctx, agg_attr=agg_attr, act="gelu", n_rows=n_rows)
+            if part is not None:
+                agg_attr = part.local(agg_attr)
+        h1 = self.graph_conv1(x, ctx=ctx, agg_attr=agg_attr, act="gelu", n_rows=n_rows, part=part)
+        h2 = self.graph_conv2(h1, ctx=ctx, agg_attr=agg_attr, act="gelu", n_rows=n_rows, part=part)
         w = split_weight(self.output_proj.weight)
         b = self.output_proj.bias.detach()
         ln1 = _ln(self.norm1)
@@ -197,20 +204,29 @@ class AdaptiveGraphPooling(nn.Module):
         return s
 
     @torch.no_grad()
-    def pool(self, x, csr, act=None):
-        """Returns (pooled_x [k,C] with `act` applied, pooled CSR, perm int32 [k], node_map int32 [N], scores)."""
+    def pool(self, x, csr, act=None, part=None):
+        """Returns (pooled_x [k,C] with `act` applied, pooled CSR, perm int32 [k], node_map int32 [N], scores, pooled Part).
+        Partitioned: scores are all-gathered, every rank runs the same exact top-k, and a selected node stays on its owner."""
         s = self.scores(x)
-        k = max(1, int(self.ratio * x.size(0)))
-        perm, node_map = ops.topk_select(s, k)
-        px = ops.pool_gather(x, s, perm, act=act)
-        return px, ops.csr_pool(csr, perm, node_map), perm, node_map, s
+        if part is None:
+            k = max(1, int(self.ratio * x.size(0)))
+            perm, node_map = ops.topk_select(s, k)
+            px = ops.pool_gather(x, s, perm, act=act)
+            return px, ops.csr_pool(csr, perm, node_map), perm, node_map, s, None
+        s_full = part.gather(s)
+        k = max(1, int(self.ratio * part.n))
+        perm, node_map = ops.topk_select(s_full, k)
+        new_part = part.pooled(node_map)
+        local_perm = (perm[new_part.a:new_part.b] - part.a).contiguous()
+        px = ops.pool_gather(x, s, local_perm, act=act)
+        return px, ops.csr_pool(csr, perm, node_map), perm, node_map, s_full, new_part
 
     @torch.no_grad()
     def forward(self, x, edge_index, edge_attr=None, batch=None):
         """Reference signature: (pooled_x, pooled_edge_index, pooled_edge_attr, perm)."""
         _require_cuda(x)
         ctx = GraphContext(edge_index, None, x.size(0))
-        px, _, perm, node_map, _ = self.pool(x, ctx.csr)
+        px, _, perm, node_map, _, _ = self.pool(x, ctx.csr)
         nm = node_map.long()
         emask = (nm[edge_index[0]] >= 0) & (nm[edge_index[1]] >= 0)      # index bookkeeping for the public API only
         pei = nm[edge_index[:, emask]]
@@ -250,28 +266,33 @@ class GraphUNet(nn.Module):
         self.final_conv = nn.Linear(hidden_channels, out_channels)
 
     @torch.no_grad()
-    def forward(self, x, edge_index=None, edge_attr=None, batch=None, *, ctx=None, return_perms=False):
+    def forward(self, x, edge_index=None, edge_attr=None, batch=None, *, ctx=None, return_perms=False, part=None):
+        """part (parallel.Part): x holds the owned rows of a node-partitioned graph; every level keeps its own Part."""
         _require_cuda(x)
         ctx = _ctx_for(x, edge_index, ctx)
         if edge_attr is not None:
             raise NotImplementedError("GraphUNet with edge attributes: pooled edge_attr aggregation is not implemented yet; "
                                       "pass edge_attr=None (the BASELINE configurations do)")
         a = self.act_name
-        csrs, xs, maps, perms = [ctx.csr], [], [], []
-        x = self.down_convs[0](x, ctx=csrs[0])
+        csrs, xs, maps, perms, parts = [ctx.csr], [], [], [], [part]
+        x = self.down_convs[0](x, ctx=csrs[0], part=parts[0])
         xs.append(x)
         # `cur` is act(x) of the reference (:419/:432) — for level 0 applied by a tiny un-pool kernel with an empty map
         cur = ops.unpool_add_act(x, x, _neg_map(x), act=a)
         for i in range(self.depth):
-            x = self.down_convs[i + 1](cur, ctx=csrs[-1])
+            x = self.down_convs[i + 1](cur, ctx=csrs[-1], part=parts[-1])
             xs.append(x)
-            cur, pcsr, perm, node_map, _ = self.pools[i].pool(x, csrs[-1], act=a)     # pooled + activated
-            csrs.append(pcsr); maps.append(node_map); perms.append(perm)
-        x = self.bottom_conv(cur, ctx=csrs[-1])
+            cur, pcsr, perm, node_map, _, ppart = self.pools[i].pool(x, csrs[-1], act=a, part=parts[-1])     # pooled + activated
+            csrs.append(pcsr); maps.append(node_map); perms.append(perm); parts.append(ppart)
+        x = self.bottom_conv(cur, ctx=csrs[-1], part=parts[-1])
         for i in range(self.depth):
             j = self.depth - 1 - i
-            cur = ops.unpool_add_act(xs[j + 1], x, maps[j], act=a)
-            x = self.up_convs[i](cur, ctx=csrs[j + 1], n_rows=cur.size(0))             # D8
+            nm = maps[j]
+            if part is not None:      # owned rows of level j; a kept node lives on the same rank at level j+1
+                nm = parts[j].local(nm)
+                nm = torch.where(nm >= 0, nm - parts[j + 1].a, nm).contiguous()
+            cur = ops.unpool_add_act(xs[j + 1], x, nm, act=a)
+            x = self.up_convs[i](cur, ctx=csrs[j + 1], n_rows=cur.size(0), part=parts[j])             # D8
         out = ops.linear(x, split_weight(self.final_conv.weight), self.final_conv.bias.detach())
         return (out, perms) if return_perms else out
 
@@ -394,19 +415,29 @@ class SpatialAttention(nn.Module):
         self.norm = nn.LayerNorm(embed_dim)
 
     @torch.no_grad()
-    def forward_nodes(self, x, pos, seg_ptr, num_seg, seg_host=None, need_weights=False, *, kv_gather=None):
-        """x [N,D], pos [N,2] for a node-sorted batch with segment pointers. Returns (out [N,D], weights list|None)."""
+    def forward_nodes(self, x, pos, seg_ptr, num_seg, seg_host=None, need_weights=False, *, part=None):
+        """x [N,D], pos [N,2] for a node-sorted batch with segment pointers. Returns (out [N,D], weights list|None).
+        part (parallel.Part): x holds the owned rows, pos / seg_ptr describe the whole batch; queries = owned rows,
+        keys / values = the all-gathered q|k|v rows (context parallelism)."""
         att = self.attention
         if self.head_dim != 16:
             raise NotImplementedError(f"SpatialAttention head_dim {self.head_dim}: only head_dim 16 (DGDM-Base) has a flash kernel in this round")
         pos = pos.float().contiguous()
-        xp = ops.spatial_pe_add(x, pos, seg_ptr, num_seg)
         w, bias = att.qkv_weight()
-        qkv = ops.linear(xp, w, bias)
-        if kv_gather is not None:
-            o = kv_gather(qkv, pos, seg_ptr, num_seg, self.num_heads, self.temperature)
-        else:
+        if part is None:
+            xp = ops.spatial_pe_add(x, pos, seg_ptr, num_seg)
+            qkv = ops.linear(xp, w, bias)
             o = ops.spatial_attention(qkv, pos, seg_ptr, num_seg, self.num_heads, self.temperature)
+        else:
+            if need_weights:
+                raise NotImplementedError("return_attention is not available for node-partitioned graphs")
+            pos_l = part.local(pos).contiguous()
+            qseg = (torch.clamp(seg_ptr, part.a, part.b) - part.a).to(torch.int32)
+            xp = ops.spatial_pe_add(x, pos_l, qseg, num_seg, minmax_from=(pos, seg_ptr))
+            qkv = ops.linear(xp, w, bias)
+            qkv_full = part.gather(qkv)
+            o = ops.spatial_attention(qkv, pos_l, qseg, num_seg, self.num_heads, self.temperature,
+                                      kv_qkv=qkv_full, kv_pos=pos, kseg_ptr=seg_ptr)
         out = ops.linear(o, split_weight(att.out_proj.weight), att.out_proj.bias.detach(), r_pre=x, ln1=_ln(self.norm))
         weights = None
         if need_weights:
@@ -666,15 +697,17 @@ class GraphEncoder(nn.Module):
         self.output_proj = nn.Linear(dims[-1], dims[-1])
 
     @torch.no_grad()
-    def forward(self, x, edge_index=None, edge_attr=None, batch=None, *, ctx=None):
+    def forward(self, x, edge_index=None, edge_attr=None, batch=None, *, ctx=None, part=None):
         _require_cuda(x)
         ctx = _ctx_for(x, edge_index, ctx)
         agg = None
         if edge_attr is not None and self.use_edge_features:
             agg = ops.edge_attr_aggregate(ctx.csr, _pad_cols(edge_attr.float(), 32))
+            if part is not None:
+                agg = part.local(agg)
         h, outs = x, []
         for i, layer in enumerate(self.graph_layers):
-            h = layer(h, ctx=ctx, agg_attr=agg,
+            h = layer(h, ctx=ctx, agg_attr=agg, part=part,
                       post=dict(transition=self.transitions[i], ln=self.norm_layers[i], act=self.activation_name))
             outs.append(h)
         final = ops.linear(h, split_weight(self.output_proj.weight), self.output_proj.bias.detach())

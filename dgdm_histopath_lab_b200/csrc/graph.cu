@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) order_rows_kernel(const long long* __rest
 template <int VPL>
 __global__ void __launch_bounds__(256) spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
                                                        const float* __restrict__ norm, const float* __restrict__ dinv,
-                                                       int n_csr_rows, int n_rows, const float* __restrict__ H, int ldh, int C,
+                                                       int n_csr_rows, int n_rows, int h_row0, const float* __restrict__ H, int ldh, int C,
                                                        const float* __restrict__ addend, int ld_add,
                                                        const float* __restrict__ bias, int act, float* __restrict__ out, int ldo) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256) spmm_gcn_kernel(const int* __restrict__ r
   for (int v = 0; v < VPL; ++v) {
     const int idx = (v * 32 + lane) * 4;
     if (idx < C) {
-      const float4 hs = ldg4(H + (size_t)row * ldh + idx);            // self loop last (add_self_loops appends)
+      const float4 hs = ldg4(H + (size_t)(h_row0 + row) * ldh + idx);  // self loop last (add_self_loops appends)
       float4 a = acc[v];
       a.x = fmaf(selfw, hs.x, a.x); a.y = fmaf(selfw, hs.y, a.y); a.z = fmaf(selfw, hs.z, a.z); a.w = fmaf(selfw, hs.w, a.w);
       if (addend) { const float4 t = ldg4(addend + (size_t)row * ld_add + idx); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
@@ -358,16 +358,16 @@ extern "C" int dgdm_csr_build(const int64_t* edge_index, int E, int N, int* rowp
 }
 
 extern "C" int dgdm_spmm_gcn(const int* rowptr, const int* col, const float* norm, const float* dinv, int n_csr_rows,
-                             int n_rows, const float* H, int ldh, int C, const float* addend, int ld_addend,
+                             int n_rows, int h_row0, const float* H, int ldh, int C, const float* addend, int ld_addend,
                              const float* bias, int act, float* out, int ldo, void* stream) {
   if (!rowptr || !dinv || !H || !out || C <= 0 || (C % 4) != 0 || C > 1024 || (ldh % 4) != 0 || (ldo % 4) != 0) return DGDM_ERR_INVALID;
   if (addend && (ld_addend % 4) != 0) return DGDM_ERR_INVALID;
   if (n_rows <= 0) return DGDM_OK;
-  if (n_csr_rows > n_rows) return DGDM_ERR_INVALID;
+  if (n_csr_rows > n_rows || h_row0 < 0) return DGDM_ERR_INVALID;
   const int blocks = (n_rows + 7) / 8;
   cudaStream_t s = (cudaStream_t)stream;
   const int vpl = (C + 127) / 128;
-#define LAUNCH_SPMM(V) spmm_gcn_kernel<V><<<blocks, 256, 0, s>>>(rowptr, col, norm, dinv, n_csr_rows, n_rows, H, ldh, C, addend, ld_addend, bias, act, out, ldo)
+#define LAUNCH_SPMM(V) spmm_gcn_kernel<V><<<blocks, 256, 0, s>>>(rowptr, col, norm, dinv, n_csr_rows, n_rows, h_row0, H, ldh, C, addend, ld_addend, bias, act, out, ldo)
   switch (vpl) {
     case 1: LAUNCH_SPMM(1); break;
     case 2: LAUNCH_SPMM(2); break;

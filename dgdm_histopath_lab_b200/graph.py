@@ -113,14 +113,16 @@ class GraphContext:
         self._key = None
 
 
-def get_context(data):
-    """Build (or fetch) the GraphContext of a data object; keyed on the identity/version of its index tensors."""
+def get_context(data, num_nodes=None):
+    """Build (or fetch) the GraphContext of a data object; keyed on the identity/version of its index tensors.
+    num_nodes: N of the whole batch when data.x holds only a rank's rows (node-partitioned execution)."""
     ei, batch = data.edge_index, getattr(data, "batch", None)
+    n = int(data.x.size(0)) if num_nodes is None else int(num_nodes)
     key = (ei.data_ptr(), ei._version, tuple(ei.shape),
-           None if batch is None else (batch.data_ptr(), batch._version, batch.numel()), int(data.x.size(0)))
+           None if batch is None else (batch.data_ptr(), batch._version, batch.numel()), n)
     ctx = data.__dict__.get("_dgdm_ctx") if hasattr(data, "__dict__") else None
     if ctx is None or ctx._key != key:
-        ctx = GraphContext(ei, batch, data.x.size(0))
+        ctx = GraphContext(ei, batch, n)
         ctx._key = key
         try:
             data.__dict__["_dgdm_ctx"] = ctx

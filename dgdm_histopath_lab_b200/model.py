@@ -128,7 +128,9 @@ class GlobalAttentionPool(nn.Module):
         self.global_token = nn.Parameter(torch.randn(1, 1, hidden_dim))
 
     @torch.no_grad()
-    def forward(self, x, batch=None, *, ctx=None, seg_ptr=None, num_seg=None):
+    def forward(self, x, batch=None, *, ctx=None, seg_ptr=None, num_seg=None, part=None):
+        """part (parallel.Part): x holds the owned rows; the k|v projections are computed on them and all-gathered (N x 2D
+        fp32), then every rank reduces the whole batch with the same kernel and order as a single GPU."""
         _require_cuda(x)
         att = self.attention
         if seg_ptr is None:
@@ -144,6 +146,8 @@ class GlobalAttentionPool(nn.Module):
         q = ops.linear(tok, split_weight(att.q_proj.weight), att.q_proj.bias.detach() if att.q_proj.bias is not None else None)
         w, b = att.kv_weight()
         kv = ops.linear(x.contiguous(), w, b)
+        if part is not None:
+            kv = part.gather(kv)
         pooled = ops.attention_pool(q.reshape(-1), kv, seg_ptr, num_seg, att.num_heads)
         return ops.linear(pooled, split_weight(att.out_proj.weight), att.out_proj.bias.detach() if att.out_proj.bias is not None else None)
 
@@ -184,30 +188,24 @@ class DGDMModel(nn.Module):
         if regression_targets > 0:
             self.regression_head = RegressionHead(hidden_dims[-1], regression_targets, [hidden_dims[-1] // 2], dropout, activation)
         self.apply(self._init_weights)
-        self._dist = None
+        self._comm = None
 
     # -------------------------------------------------------------------------------------- multi-GPU
-    def set_distributed(self, rank, world, group=None):
-        """One process per GPU (torch.distributed, NCCL). The O(N^2) spatial attention — ~90% of the forward at 100k nodes —
-        is sharded by query rows (each rank keeps the full K/V, which it computes itself: 2 x N x 128 fp16 = 51 MB at 100k),
-        its [N/P, D] outputs are all-gathered over NVLink; the O(N) encoder / U-Net are replicated."""
-        self._dist = (int(rank), int(world), group) if world and world > 1 else None
+    def set_partition(self, comm):
+        """Node-partitioned execution over the ranks of `comm` (parallel.TorchDistComm for one process per GPU over NCCL;
+        parallel.ThreadComm for in-process test ranks); None or a 1-rank comm restores single-GPU execution.
+        In this mode `data.edge_index`, `data.pos`, `data.batch` describe the WHOLE graph batch on every rank and `data.x`
+        holds either all rows or only the rows this rank owns (then `data.num_nodes` gives N); `node_embeddings` in the
+        output are the owned rows, `node_range` their (start, stop). See parallel.py for the design."""
+        self._comm = comm if comm is not None and comm.world > 1 else None
 
-    def _dist_attention(self, qkv, pos, seg_ptr, num_seg, heads, temperature):
-        import torch.distributed as dist
-        rank, world, group = self._dist
-        n, d3 = qkv.shape
-        rows = -(-n // world)
-        r0, r1 = min(n, rank * rows), min(n, (rank + 1) * rows)
-        out = torch.zeros(rows, d3 // 3, dtype=torch.float32, device=qkv.device)
-        if r1 > r0:
-            qseg = (torch.clamp(seg_ptr, r0, r1) - r0).to(torch.int32)
-            o = ops.spatial_attention(qkv[r0:r1], pos[r0:r1].contiguous(), qseg, num_seg, heads, temperature,
-                                      kv_qkv=qkv, kv_pos=pos, kseg_ptr=seg_ptr)
-            out[:r1 - r0] = o
-        full = torch.empty(world * rows, d3 // 3, dtype=torch.float32, device=qkv.device)
-        dist.all_gather_into_tensor(full, out, group=group)
-        return full[:n]
+    def set_distributed(self, rank, world, group=None):
+        """Convenience for torchrun launches: partition over the default (or given) torch.distributed group."""
+        if world and world > 1:
+            from .parallel import TorchDistComm
+            self.set_partition(TorchDistComm(group))
+        else:
+            self.set_partition(None)
 
     # -------------------------------------------------------------------------------------- construction
     def _validate_configuration(self, node_features, hidden_dims, num_diffusion_steps, attention_heads, dropout, graph_layers,
@@ -281,7 +279,7 @@ class DGDMModel(nn.Module):
         _require_cuda(x)
         if x.dtype != torch.float32 or ei.dtype != torch.int64 or not ei.is_cuda:
             raise ValidationError("x must be float32 and edge_index int64, both on the CUDA device")
-        flags, stats = ops.validate_inputs(x.contiguous(), ei.contiguous(), x.size(0))     # one kernel, one readback
+        flags, stats = ops.validate_inputs(x.contiguous(), ei.contiguous(), self._num_nodes(data))   # one kernel, one readback
         if flags[0]:
             raise ValidationError("Node features contain NaN values")
         if flags[1]:
@@ -318,32 +316,52 @@ class DGDMModel(nn.Module):
         except Exception as e:
             raise ModelInferenceError(f"Forward pass failed: {e}") from e
 
+    def _num_nodes(self, data):
+        """N of the whole batch: x may hold only the owned rows of a node-partitioned graph."""
+        if self._comm is None:
+            return int(data.x.size(0))
+        n = data.__dict__.get("_num_nodes") if hasattr(data, "__dict__") else None
+        if n is None:
+            pos, batch = getattr(data, "pos", None), getattr(data, "batch", None)
+            n = pos.size(0) if pos is not None else (batch.numel() if batch is not None else data.x.size(0))
+        return int(n)
+
     def _forward_impl(self, data, mode, return_attention, return_embeddings, rng):
         x = data.x.contiguous()
-        ctx = get_context(data)
+        N = self._num_nodes(data)
+        ctx = get_context(data, N)
         batch = getattr(data, "batch", None)
         pos = getattr(data, "pos", None)
         edge_attr = getattr(data, "edge_attr", None)
-        inv = None
         if batch is not None and not ctx.sorted:
             # node-sorted segments are what the kernels index; the reference's boolean masks accept any order
             raise ModelInferenceError("batch vector must be sorted by graph id (Batch.from_data_list produces this)")
+        part = None
+        if self._comm is not None:
+            from .parallel import Part, even_bounds
+            if mode == "pretrain":
+                raise ModelInferenceError("mode='pretrain' is not available for node-partitioned graphs (inference / finetune are)")
+            part = Part(self._comm, even_bounds(N, self._comm.world))
+            if x.size(0) == N and part.n_local != N:
+                x = x[part.a:part.b]
+            elif x.size(0) != part.n_local:
+                raise ModelInferenceError(f"rank {self._comm.rank} owns rows [{part.a}, {part.b}) but data.x has {x.size(0)} rows")
         h = self.feature_encoder(x)
-        h = self.graph_encoder(h, ctx=ctx, edge_attr=edge_attr)["embeddings"]
+        h = self.graph_encoder(h, ctx=ctx, edge_attr=edge_attr, part=part)["embeddings"]
         outputs, attn = {}, None
         if self.spatial_attention is not None and pos is not None:
-            h, attn = self.spatial_attention.forward_nodes(h, pos, ctx.seg_ptr, ctx.num_graphs, ctx.seg_host, return_attention,
-                                                           kv_gather=self._dist_attention if self._dist is not None else None)
+            h, attn = self.spatial_attention.forward_nodes(h, pos, ctx.seg_ptr, ctx.num_graphs, ctx.seg_host, return_attention, part=part)
             if attn is not None and batch is None:
                 attn = attn[0]
         if self.hierarchical_processor is not None:
-            h = self.hierarchical_processor(h, ctx=ctx, edge_attr=edge_attr)
+            h = self.hierarchical_processor(h, ctx=ctx, edge_attr=edge_attr, part=part)
         if mode == "pretrain":
             outputs.update(self._compute_diffusion_loss(h, ctx, rng))
         if isinstance(self.global_pool, GlobalAttentionPool):
-            g = self.global_pool(h, ctx=ctx)
+            g = self.global_pool(h, ctx=ctx, part=part)
         else:
-            g = self.global_pool(h, batch, ctx=ctx if batch is not None else None)
+            h_pool = h if part is None else part.gather(h)
+            g = self.global_pool(h_pool, batch, ctx=ctx if batch is not None else None)
         if self.classification_head is not None and mode in ("inference", "finetune"):
             logits = self.classification_head(g)
             outputs["classification_logits"] = logits
@@ -353,6 +371,8 @@ class DGDMModel(nn.Module):
         outputs["graph_embedding"] = g
         if return_embeddings:
             outputs["node_embeddings"] = h
+            if part is not None:
+                outputs["node_range"] = part.rows
         if return_attention and attn is not None:
             outputs["attention_weights"] = attn
         return outputs

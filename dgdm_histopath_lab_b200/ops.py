@@ -200,16 +200,25 @@ def csr_build(edge_index, N):
     return CSR(rowptr, col, eid, norm, dinv, N, E)
 
 
-def spmm_gcn(csr, h, *, n_rows=None, addend=None, bias=None, act=None, out=None):
+def spmm_gcn(csr, h, *, n_rows=None, rows=None, addend=None, bias=None, act=None, out=None):
+    """GCN propagate. Single GPU: rows [0, n_rows) of `h`. Node-partitioned: rows=(a, b) are the output rows this rank owns,
+    `h` is the all-gathered feature matrix (global row indices), out/addend are local [b-a, C]."""
     lib = _lib.load()
-    n_rows = csr.N if n_rows is None else n_rows
     Cw = h.size(1)
-    assert h.stride(1) == 1 and h.size(0) >= n_rows
+    if rows is None:
+        a, n_rows = 0, (csr.N if n_rows is None else n_rows)
+    else:
+        a, n_rows = int(rows[0]), int(rows[1]) - int(rows[0])
+    n_csr = max(0, min(csr.N - a, n_rows))
+    assert h.stride(1) == 1 and h.size(0) >= a + n_rows
     if out is None:
         out = torch.empty(n_rows, Cw, dtype=torch.float32, device=h.device)
     if _PROFILE is not None:      # profiling pass only: the edge count of pooled levels lives on the device
-        _PROFILE_META.setdefault("spmm", []).append((n_rows, int(csr.rowptr[min(csr.N, n_rows)].item()), Cw))
-    _check(lib.dgdm_spmm_gcn(_p(csr.rowptr), _p(csr.col), _p(csr.norm), _p(csr.dinv), min(csr.N, n_rows), n_rows,
+        e0 = int(csr.rowptr[min(csr.N, a)].item()); e1 = int(csr.rowptr[min(csr.N, a + n_rows)].item())
+        _PROFILE_META.setdefault("spmm", []).append((n_rows, e1 - e0, Cw))
+    a_csr = min(a, csr.N)          # rows beyond the CSR (D8) never dereference rowptr/dinv
+    _check(lib.dgdm_spmm_gcn(C.c_void_p(csr.rowptr.data_ptr() + 4 * a_csr), _p(csr.col), _p(csr.norm),
+                             C.c_void_p(csr.dinv.data_ptr() + 4 * min(a_csr, max(csr.N - 1, 0))), n_csr, n_rows, a,
                              _p(_f32c(h)), h.stride(0), Cw, _p(addend), addend.stride(0) if addend is not None else 0,
                              _p(bias), ACT[act], _p(out), out.stride(0), _stream()), "dgdm_spmm_gcn")
     return out
@@ -277,11 +286,14 @@ def segment_softmax_scores(csr, qkv, ek, hid, heads):
 
 
 # ------------------------------------------------------------------------------------------------ attention
-def spatial_pe_add(x, pos, seg_ptr, num_seg):
+def spatial_pe_add(x, pos, seg_ptr, num_seg, minmax_from=None):
+    """minmax_from = (full_pos, full_seg_ptr): per-segment min/max taken over the whole batch while x / pos / seg_ptr describe
+    only the rows this rank owns (node-partitioned graphs)."""
     lib = _lib.load()
     N, D = x.shape
     minmax = torch.empty(num_seg, 2, dtype=torch.float32, device=x.device)
-    _check(lib.dgdm_segment_minmax(_p(_f32c(pos)), _p(seg_ptr), num_seg, _p(minmax), _stream()), "dgdm_segment_minmax")
+    mm_pos, mm_seg = (pos, seg_ptr) if minmax_from is None else minmax_from
+    _check(lib.dgdm_segment_minmax(_p(_f32c(mm_pos)), _p(mm_seg), num_seg, _p(minmax), _stream()), "dgdm_segment_minmax")
     out = torch.empty(N, D, dtype=torch.float32, device=x.device)
     _check(lib.dgdm_spatial_pe_add(_p(_f32c(x)), x.stride(0), _p(pos), _p(seg_ptr), num_seg, _p(minmax), N, D, _p(out),
                                    out.stride(0), _stream()), "dgdm_spatial_pe_add")

@@ -89,12 +89,14 @@ size_t dgdm_csr_build_work_ints(int N, int E);
 int dgdm_csr_build(const int64_t* edge_index, int E, int N, int* rowptr, int* col, int* eid, float* norm,
                    float* dinv, int* work, void* stream);
 
-/* GraphConvolution.propagate + bias + activation (core/graph_layers.py:92-110, 233-239):
- *   out[i,:] = act( sum_{e in row i, edge order} norm[e]*H[col[e],:] + dinv[i]^2*H[i,:] (+addend[i,:]) (+bias) )
+/* GraphConvolution.propagate + bias + activation (core/graph_layers.py:92-110, 233-239) for output rows i in [0, n_rows):
+ *   out[i,:] = act( sum_{e in row i, edge order} norm[e]*H[col[e],:] + dinv[i]^2*H[h_row0+i,:] (+addend[i,:]) (+bias) )
  * Rows i >= n_csr_rows (decoder levels of GraphUNet, D8) have only the self loop with weight 1.
+ * Node-partitioned graphs: a rank that owns rows [a,b) passes rowptr+a, dinv+a, h_row0 = a and the all-gathered H
+ * (col holds global indices); single GPU: h_row0 = 0.
  * C % 4 == 0, C <= 1024. Deterministic: fixed in-row order, self loop last, no atomics. */
 int dgdm_spmm_gcn(const int* rowptr, const int* col, const float* norm, const float* dinv, int n_csr_rows,
-                  int n_rows, const float* H, int ldh, int C, const float* addend, int ld_addend,
+                  int n_rows, int h_row0, const float* H, int ldh, int C, const float* addend, int ld_addend,
                   const float* bias, int act, float* out, int ldo, void* stream);
 
 /* sum_{e in row i} norm[e]*edge_attr[eid[e],:]  -> agg[N, D]  (identity (i) of SURVEY §8: the edge_lin term of

@@ -117,6 +117,7 @@ def main():
     ap.add_argument("--ref-nodes", type=int, default=2000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fused-halo", action="store_true", help="multi-GPU: NCCL all-gather per propagate instead of the GEMM-epilogue P2P/multicast stores")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -133,6 +134,8 @@ def main():
     ops.device_check(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # stdout carries exactly one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=dev)
 
     with warnings.catch_warnings():
@@ -140,11 +143,18 @@ def main():
         model = DGDMModel(**BASE_CFG).eval()
     model.load_state_dict(synth.seeded_state_dict(model, 0))
     model = model.to(dev)
-    if world > 1:
-        model.set_distributed(rank, world)
     host = synth.tile_graph(args.nodes, 768, seed=1234)
     N, E = host.x.size(0), host.edge_index.size(1)
-    data = host.to(dev)
+    rows = None
+    if world > 1:
+        # 1-D node partition (parallel.py): every rank holds the graph structure and pos, and only its own rows of x
+        from dgdm_histopath_lab_b200.parallel import even_bounds
+        model.set_distributed(rank, world, max_nodes=N, fused=not args.no_fused_halo)
+        b = even_bounds(N, world)
+        rows = (b[rank], b[rank + 1])
+        data = Data(x=host.x[rows[0]:rows[1]].to(dev), edge_index=host.edge_index.to(dev), pos=host.pos.to(dev), num_nodes=N)
+    else:
+        data = host.to(dev)
 
     def barrier():
         if world > 1:
@@ -164,8 +174,10 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    th0 = time.perf_counter()
     for _ in range(args.steps):
         out = step_resident()
+    host_ms = 1e3 * (time.perf_counter() - th0) / args.steps      # CPU time to enqueue one forward (no device sync inside)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -177,23 +189,26 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     value = N * args.steps / (ms / 1e3)
 
-    # ---- end to end through the public API with host buffers
+    # ---- end to end through the public API with host buffers: every step copies that step's inputs from pinned host memory
+    # (this rank's rows of x + the graph structure) and reads the graph embedding back; DevicePrefetcher stages step i+1 on
+    # a side stream while step i computes, the CSR is rebuilt every step because the inputs are new tensors.
     e2e = None
     if not args.no_e2e:
-        hx, hei, hpos = host.x.pin_memory(), host.edge_index.pin_memory(), host.pos.pin_memory()
-        h2d = hx.numel() * 4 + hei.numel() * 8 + hpos.numel() * 4
+        from dgdm_histopath_lab_b200.loader import DevicePrefetcher
+        hg = Data(x=host.x.pin_memory(), edge_index=host.edge_index.pin_memory(), pos=host.pos.pin_memory())
+        nx = N if rows is None else rows[1] - rows[0]
+        h2d = nx * 768 * 4 + hg.edge_index.numel() * 8 + hg.pos.numel() * 4
 
-        def step_e2e():
-            d = Data(x=hx.to(dev, non_blocking=True), edge_index=hei.to(dev, non_blocking=True), pos=hpos.to(dev, non_blocking=True))
-            o = model(d)
-            return o["graph_embedding"].cpu()
+        def run_e2e(k):
+            g = None
+            for d in DevicePrefetcher([hg] * k, dev, rows=rows):
+                g = model(d)["graph_embedding"].cpu()
+            return g
 
-        for _ in range(2):
-            g = step_e2e()
+        run_e2e(2)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            g = step_e2e()
+        g = run_e2e(args.steps)
         barrier()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -201,7 +216,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": N * args.steps / dt, "unit": "nodes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": g.numel() * 4,
-               "ms_per_step": 1e3 * dt / args.steps}
+               "ms_per_step": 1e3 * dt / args.steps, "staging": "pinned host -> device on a side stream, one step ahead"}
 
     # ---- per-kernel-class timing pass (CUDA events after every C-ABI call on the launching stream)
     pk = peaks()
@@ -221,6 +236,13 @@ def main():
             "peak": pk["tf_sustained"], "unit": "TFLOP/s", "traffic": None, "peak_source": pk["src"],
             "note": "dominant kernel; exp2(MUFU)-bound, not tensor- or HBM-bound: head_dim 16 gives K=16 / N=16 MMAs",
             "gexp_per_s": att_exp / (att_ms * 1e-3) / 1e9 if att_ms else None, "ms": att_ms}
+    # the bound that actually applies: MUFU (XU pipe, 16 lanes/clk/SM): one exp2 per score + one sqrt per (row, key) per 4-head
+    # softmax group = 1.25 MUFU ops per score
+    sm_clock_ghz = ((clocks or {}).get("sm_mhz") or 1965) / 1e3
+    mufu_peak = 148 * 16 * sm_clock_ghz                      # G ops/s at the SM clock sampled during the run
+    if att_ms:
+        roof["mufu"] = {"achieved_gops": 1.25 * att_exp / (att_ms * 1e-3) / 1e9, "peak_gops": mufu_peak,
+                        "frac": 1.25 * att_exp / (att_ms * 1e-3) / 1e9 / mufu_peak, "ops_per_score": 1.25}
     roof["frac"] = roof["achieved"] / roof["peak"] if roof["achieved"] else None
     roof_hbm = {"kernel": "spmm_gcn_kernel (all launches)", "bound": "hbm", "achieved": spmm_bytes / (spmm_ms * 1e-3) / 1e9 if spmm_ms else None,
                 "peak": pk["hbm"], "unit": "GB/s", "traffic": None, "ms": spmm_ms, "launches": len(meta.get("spmm", [])),
@@ -243,10 +265,11 @@ def main():
                 "config": {"workload": f"DGDM-Base forward (eval, inference mode, return_embeddings) on one synthetic {N}-node 768-d tile graph, "
                                        f"E={E} directed edges, random-init seeded weights", "nodes": N, "edges": E,
                            "l2_policy": "inputs larger than L2 (x = 307 MB, activations > 200 MB per layer)",
-                           "parallelism": "single GPU" if world == 1 else f"spatial attention sharded by query rows over {world} GPUs "
-                                          f"(NCCL all-gather of outputs), encoder/U-Net replicated",
-                           "attention_precise": ops.attention_precise_default(), "gemm": ops.gemm_mode()},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "roofline_hbm": roof_hbm, "roofline_gemm": roof_gemm,
+                           "parallelism": "single GPU" if world == 1 else f"1-D node partition over {world} GPUs: features row-partitioned, NCCL all-gather "
+                                          f"of projected rows per propagate (halo), context-parallel attention, replicated graph structure",
+                           "attention_precise": ops.attention_precise_default(), "gemm": ops.gemm_mode(),
+                           "halo": None if world == 1 else type(model._comm).__name__ + ("/multicast" if getattr(model._comm, "multicast", False) else "")},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms, "roofline": roof, "roofline_hbm": roof_hbm, "roofline_gemm": roof_gemm,
                 "cpu_baseline": cpu, "per_call_ms": {k: round(v[1], 4) for k, v in prof.items()},
                 "graph_embedding_checksum": float(out["graph_embedding"].double().abs().sum().item())}
         print(json.dumps(line), flush=True)

@@ -27,6 +27,7 @@ class GemmParams(C.Structure):
         ("dot_w", c_void_p), ("dot_b", c_float), ("dot_act", c_int), ("dot_out", c_void_p),
         ("a_scale", c_float),
         ("row_bias_index", c_void_p), ("row_bias", c_void_p), ("ld_row_bias", c_int),
+        ("C_peers", c_void_p * 8), ("n_peers", c_int), ("peers_multicast", c_int),
     ]
 
 

@@ -112,10 +112,18 @@ class GraphConvolution(nn.Module):
         _require_cuda(x)
         ctx = _ctx_for(x, edge_index, ctx)
         csr = ctx.csr if isinstance(ctx, GraphContext) else ctx
-        h = ops.linear(x, split_weight(self.node_lin.weight))
-        rows = None
+        rows, h = None, None
         if part is not None:
-            h, rows, n_rows = part.gather(h), part.rows, None
+            rows, n_rows = part.rows, None
+            fused = getattr(part.comm, "fused_linear_gather", None)
+            if fused is not None and self.out_channels <= 512:
+                # GEMM -> all-gather in one kernel: the epilogue stores each tile into every rank's copy over NVLink
+                w = split_weight(self.node_lin.weight)
+                h = fused(lambda out, peers, mc: ops.linear(x, w, out=out, peers=peers, multicast=mc), part, self.out_channels)
+            if h is None:
+                h = part.gather(ops.linear(x, split_weight(self.node_lin.weight)))
+        else:
+            h = ops.linear(x, split_weight(self.node_lin.weight))
         addend = None
         if self.edge_lin is not None and (edge_attr is not None or agg_attr is not None):
             if agg_attr is None:

@@ -78,9 +78,13 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
 }
 
 // ---- per-warp 32x32 transposing I/O through smem ----
-// thread-row-owned regs v[32] (row = lane) -> coalesced global store of rows [row0, row0+32), cols [c0, c0+32)
-__device__ __forceinline__ void warp_store_tile(float* st, const float* v, float* G, int ldg, int row0, int c0,
-                                                int M, int N, int lane) {
+__device__ __forceinline__ void multimem_st4(float* mc, float4 t) {
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
+}
+// thread-row-owned regs v[32] (row = lane) -> coalesced global store of rows [row0, row0+32), cols [c0, c0+32).
+// Node-partitioned graphs: the same 128-byte row segments also go to the peers' copies of C (P2P stores over NVLink, or one
+// NVLS multicast store that the switch replicates to every rank) — the halo all-gather fused into the GEMM epilogue.
+__device__ __forceinline__ void warp_store_tile(float* st, const float* v, const dgdm_gemm_params& p, int row0, int c0, int lane) {
 #pragma unroll
   for (int j = 0; j < 8; ++j)
     *reinterpret_cast<float4*>(st + lane * TR_STRIDE + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -89,7 +93,17 @@ __device__ __forceinline__ void warp_store_tile(float* st, const float* v, float
   for (int it = 0; it < 8; ++it) {
     int r = it * 4 + (lane >> 3), c = (lane & 7) * 4;
     float4 t = *reinterpret_cast<const float4*>(st + r * TR_STRIDE + c);
-    if (row0 + r < M && c0 + c < N) *reinterpret_cast<float4*>(G + (size_t)(row0 + r) * ldg + c0 + c) = t;
+    if (row0 + r < p.M && c0 + c < p.N) {
+      const size_t off = (size_t)(row0 + r) * p.ldc + c0 + c;
+      if (p.n_peers == 0) {
+        *reinterpret_cast<float4*>(p.C + off) = t;
+      } else if (p.peers_multicast) {
+        multimem_st4(p.C_peers[0] + off, t);
+      } else {
+        *reinterpret_cast<float4*>(p.C + off) = t;
+        for (int d = 0; d < p.n_peers; ++d) *reinterpret_cast<float4*>(p.C_peers[d] + off) = t;
+      }
+    }
   }
   __syncwarp();
 }
@@ -147,7 +161,7 @@ __device__ __forceinline__ void epilogue_rows(const dgdm_gemm_params& p, const E
 #pragma unroll
       for (int j = 0; j < 32; ++j) dot = fmaf(v[j], t[j], dot);
     }
-    if (p.C != nullptr) warp_store_tile(st, v, p.C, p.ldc, row0, c0, p.M, p.N, lane);
+    if (p.C != nullptr) warp_store_tile(st, v, p, row0, c0, lane);
   };
   auto normalise = [&](int c0, const float* g, const float* b, float mean, float rstd) {
     lds_row32(g + c0, t);
@@ -507,6 +521,8 @@ extern "C" int dgdm_gemm_f16x2(const dgdm_gemm_params* p, void* stream) {
   if (p->r_post && (p->ld_r_post % 4) != 0) return DGDM_ERR_INVALID;
   if ((p->ln1_g == nullptr) != (p->ln1_b == nullptr) || (p->ln2_g == nullptr) != (p->ln2_b == nullptr)) return DGDM_ERR_INVALID;
   if (!(p->a_scale > 0.f)) return DGDM_ERR_INVALID;
+  if (p->n_peers < 0 || p->n_peers > 8 || (p->n_peers > 0 && (!p->C || p->N > 512))) return DGDM_ERR_INVALID;
+  for (int d = 0; d < p->n_peers; ++d) if (!p->C_peers[d]) return DGDM_ERR_INVALID;
   const long long plane_stride = (long long)p->N * 128;
   if (p->N <= 512) return launch_gemm(*p, plane_stride, (cudaStream_t)stream);
   // Rows wider than TMEM (DGDM-Large 768-d layers): raw products in column groups of <= 512, then the stand-alone

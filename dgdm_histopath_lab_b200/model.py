@@ -199,13 +199,21 @@ class DGDMModel(nn.Module):
         output are the owned rows, `node_range` their (start, stop). See parallel.py for the design."""
         self._comm = comm if comm is not None and comm.world > 1 else None
 
-    def set_distributed(self, rank, world, group=None):
-        """Convenience for torchrun launches: partition over the default (or given) torch.distributed group."""
-        if world and world > 1:
-            from .parallel import TorchDistComm
-            self.set_partition(TorchDistComm(group))
-        else:
-            self.set_partition(None)
+    def set_distributed(self, rank, world, group=None, max_nodes=None, fused=True):
+        """Convenience for torchrun launches: partition over the default (or given) torch.distributed group. With
+        max_nodes (the largest N that will be seen) and CUDA peer access the halo exchange is fused into the GEMM epilogue
+        (parallel.SymmComm); otherwise it is an NCCL all-gather per propagate."""
+        if not world or world <= 1:
+            return self.set_partition(None)
+        from .parallel import SymmComm, TorchDistComm
+        comm = None
+        if fused and max_nodes and next(self.parameters()).is_cuda:
+            width = max([self.hidden_dims[0]] + list(self.hidden_dims))
+            try:
+                comm = SymmComm(int(max_nodes) * min(width, 512), next(self.parameters()).device, group)
+            except Exception as e:      # no P2P / symmetric memory on this box: NCCL path (still correct, just slower)
+                warnings.warn(f"symmetric-memory halo exchange unavailable ({e}); using NCCL all-gather")
+        self.set_partition(comm if comm is not None else TorchDistComm(group))
 
     # -------------------------------------------------------------------------------------- construction
     def _validate_configuration(self, node_features, hidden_dims, num_diffusion_steps, attention_heads, dropout, graph_layers,

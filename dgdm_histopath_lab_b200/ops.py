@@ -116,11 +116,13 @@ def gemm_mode():
 
 
 def linear(a, w, bias=None, *, r_pre=None, act_pre=None, ln1=None, ln2=None, act_post=None, r_post=None,
-           dot=None, out=None, want_out=True, ln_eps=1e-5, row_bias=None, a_scale=1.0, mode=None):
+           dot=None, out=None, want_out=True, ln_eps=1e-5, row_bias=None, a_scale=1.0, mode=None, peers=None, multicast=False):
     """out = epilogue(a @ w^T). a [M,K] fp32 (row stride may exceed K), w SplitWeight [N,K].
 
     ln1/ln2: (gamma, beta) tuples. dot: (w_vec [N], b float, act) -> also returns dot_out [M].
     row_bias: (index int32 [M], table [R,N]). Returns out, or (out, dot_out) when dot is given.
+    peers: addresses (ints) of the peers' copies of `out` (symmetric memory) — the epilogue stores every tile there as well
+    (fused halo all-gather); multicast=True: peers[0] is an NVLS multicast address covering all ranks incl. this one.
     """
     lib = _lib.load()
     mode = mode or gemm_mode()
@@ -161,6 +163,11 @@ def linear(a, w, bias=None, *, r_pre=None, act_pre=None, ln1=None, ln2=None, act
     if row_bias is not None:
         keep = row_bias
         p.row_bias_index, p.row_bias, p.ld_row_bias = _p(row_bias[0]), _p(row_bias[1]), row_bias[1].stride(0)
+    if peers:
+        assert out is not None and mode != "simt" and N <= 512 and len(peers) <= 8
+        for i, a_ in enumerate(peers):
+            p.C_peers[i] = int(a_)
+        p.n_peers, p.peers_multicast = len(peers), int(bool(multicast))
     if _PROFILE is not None:
         _PROFILE_META.setdefault("gemm", []).append((M, K, N))
     if M > 0:

@@ -74,6 +74,50 @@ class TorchDistComm(Comm):
         self._dist.barrier(group=self.group)
 
 
+class SymmComm(TorchDistComm):
+    """TorchDistComm + the fused halo exchange: the projected rows of a GraphConvolution are written by the GEMM epilogue
+    itself into every rank's copy of the [N, C] matrix — P2P stores over NVLink into symmetric memory, or one NVLS multicast
+    store per tile when the switch supports it — so the all-gather costs no extra kernel and overlaps the GEMM tile by tile.
+    Two symmetric buffers alternate between consecutive convolutions; a device-side barrier (signal pads, on the compute
+    stream) separates the stores of convolution k from the SpMM that reads them, and — because every rank passes barrier
+    k+1 only after its own SpMM k — also protects buffer k%2 from being overwritten by convolution k+2 while still in use."""
+
+    def __init__(self, max_floats, device, group=None, use_multicast=True):
+        super().__init__(group)
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self._pg = group if group is not None else dist.group.WORLD
+        self.max_floats = int(max_floats)
+        self.bufs, self.hdls = [], []
+        for _ in range(2):
+            t = symm_mem.empty(self.max_floats, dtype=torch.float32, device=device)
+            self.hdls.append(symm_mem.rendezvous(t, self._pg))
+            self.bufs.append(t)
+        self.multicast = bool(use_multicast) and all(int(getattr(h, "multicast_ptr", 0) or 0) != 0 for h in self.hdls)
+        self._k = 0
+
+    def fused_linear_gather(self, linear_fn, part, n_cols):
+        """linear_fn(out, peers, multicast) runs the GEMM whose epilogue writes this rank's rows [a, b) of the [n, n_cols]
+        matrix into `out` (a view of the local symmetric buffer) and into the peers' buffers. Returns the full matrix."""
+        need = part.n * n_cols
+        if need > self.max_floats:
+            return None
+        i = self._k & 1
+        self._k += 1
+        buf, hdl = self.bufs[i], self.hdls[i]
+        full = buf[:need].view(part.n, n_cols)
+        out = full[part.a:part.b]
+        off = part.a * n_cols * 4
+        if self.multicast:
+            peers, mc = [int(hdl.multicast_ptr) + off], True
+        else:
+            peers, mc = [int(hdl.buffer_ptrs[r]) + off for r in range(self.world) if r != self.rank], False
+        if part.n_local > 0:
+            linear_fn(out, peers, mc)
+        hdl.barrier(channel=0)
+        return full
+
+
 class ThreadComm(Comm):
     """In-process ranks (one Python thread each, one shared GPU) for tests: the exchange is a device synchronise + a
     threading.Barrier around a shared slot list. Create with ThreadComm.make(world) -> list of per-rank comms."""

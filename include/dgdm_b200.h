@@ -65,6 +65,12 @@ typedef struct {
   const float* dot_w; float dot_b; int dot_act; float* dot_out;   /* row-dot epilogue (NULL = skip) */
   float a_scale;                                  /* power of two applied to A before the fp16 split (1.0f default) */
   const int* row_bias_index; const float* row_bias; int ld_row_bias; /* optional per-row bias: v += row_bias[row_bias_index[m], :] */
+  /* Fused halo exchange for node-partitioned graphs (GEMM -> all-gather in ONE kernel over NVLink peer memory): every
+   * output tile is also stored at the same (row, column, ldc) position of n_peers peer buffers — C_peers[i] is the address
+   * in THIS process of the peer's copy of C (symmetric memory, P2P mapped). peers_multicast = 1: C_peers[0] is an NVLS
+   * multicast address that covers every rank including this one (one multimem.st per tile, the switch replicates it) and
+   * the plain store to C is skipped. n_peers = 0 (default): ordinary single-GPU store. */
+  float* C_peers[8]; int n_peers; int peers_multicast;
 } dgdm_gemm_params;
 
 /* tcgen05 + TMEM path (the product path). */

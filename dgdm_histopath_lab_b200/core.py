@@ -381,10 +381,9 @@ class MultiHeadAttention(nn.Module):
             dev = query.device
             qseg = torch.tensor([0, L], dtype=torch.int32, device=dev)
             kseg = torch.tensor([0, Lk], dtype=torch.int32, device=dev)
-            if self.head_dim == 16:
-                o = ops.spatial_attention(qkv, None, qseg, 1, self.num_heads, kv_qkv=kv_qkv, kseg_ptr=kseg)
-            else:
-                raise NotImplementedError(f"head_dim {self.head_dim}: only head_dim 16 has a flash kernel in this round")
+            if self.head_dim not in (4, 8, 16, 32, 64):
+                raise NotImplementedError(f"head_dim {self.head_dim}: supported head widths are 4, 8, 16, 32, 64")
+            o = ops.spatial_attention(qkv, None, qseg, 1, self.num_heads, kv_qkv=kv_qkv, kseg_ptr=kseg)
             o = ops.linear(o, split_weight(self.out_proj.weight), self.out_proj.bias.detach() if self.out_proj.bias is not None else None)
             outs.append(o)
             if need_weights:
@@ -428,8 +427,8 @@ class SpatialAttention(nn.Module):
         part (parallel.Part): x holds the owned rows, pos / seg_ptr describe the whole batch; queries = owned rows,
         keys / values = the all-gathered q|k|v rows (context parallelism)."""
         att = self.attention
-        if self.head_dim != 16:
-            raise NotImplementedError(f"SpatialAttention head_dim {self.head_dim}: only head_dim 16 (DGDM-Base) has a flash kernel in this round")
+        if self.head_dim not in (4, 8, 16, 32, 64):
+            raise NotImplementedError(f"SpatialAttention head_dim {self.head_dim}: supported head widths are 4, 8, 16, 32, 64")
         pos = pos.float().contiguous()
         w, bias = att.qkv_weight()
         if part is None:

@@ -570,6 +570,10 @@ void attn_launch_combine(const float* Opart, const float* Mpart, const float* Lp
                          float* out, int ldo, cudaStream_t s) {
   attn_combine_kernel<<<agrid((size_t)Nq * (D / 4)), 256, 0, s>>>(Opart, Mpart, Lpart, nsplit, Nq, D, heads, out, ldo);
 }
+// attention_simt.cu: exact fp32 CUDA-core path for head dimensions other than 16 (DGDM-Large: 16 heads x 8)
+int attn_simt_launch(const float* q_qkv, int ld_q, const float* q_pos, const int* qseg_ptr, int Nq,
+                     const float* kv_qkv, int ld_kv, const float* kv_pos, const int* kseg_ptr, int num_seg,
+                     int D, int heads, float temperature, float* out, int ldo, cudaStream_t s);
 // attention_tc.cu: tcgen05 / TMEM path (D = 128, 8 heads)
 size_t attn_tc_work_bytes(int Nq, int Nkv, int D, int heads, int num_seg);
 int attn_tc_launch(const float* q_qkv, int ld_q, const float* q_pos, const int* qseg_ptr, int Nq,
@@ -599,10 +603,13 @@ extern "C" int dgdm_spatial_attention(const float* q_qkv, int ld_q, const float*
                                       int num_seg, int D, int heads, float temperature, int precise,
                                       float* out, int ldo, void* work, size_t work_bytes, void* stream) {
   if (!q_qkv || !kv_qkv || !qseg_ptr || !kseg_ptr || !out || !work) return DGDM_ERR_INVALID;
-  if (heads <= 0 || D % heads != 0 || D / heads != 16 || (ldo % 4) != 0) return DGDM_ERR_INVALID;   // head_dim 16 only (Base)
+  if (heads <= 0 || D % heads != 0 || (ldo % 4) != 0) return DGDM_ERR_INVALID;
   if ((q_pos == nullptr) != (kv_pos == nullptr)) return DGDM_ERR_INVALID;
   if (Nq <= 0) return DGDM_OK;
   if (Nkv <= 0 || num_seg <= 0 || !(temperature > 0.f)) return DGDM_ERR_INVALID;
+  if (D / heads != 16 || precise == 3)      // other head widths (DGDM-Large 16 x 8) / forced: exact fp32 CUDA-core kernel
+    return attn_simt_launch(q_qkv, ld_q, q_pos, qseg_ptr, Nq, kv_qkv, ld_kv, kv_pos, kseg_ptr, num_seg, D, heads, temperature, out, ldo,
+                            (cudaStream_t)stream);
   if (work_bytes < dgdm_spatial_attention_work_bytes(Nq, Nkv, D, heads, num_seg)) return DGDM_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
   if (precise == 1 && D == 128 && heads == 8)       // product path for DGDM-Base: tcgen05 / TMEM kernel (attention_tc.cu)

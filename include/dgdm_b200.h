@@ -148,7 +148,8 @@ int dgdm_spatial_pe_add(const float* X, int ldx, const float* pos, const int* se
  * query's segment in qseg_ptr.  work: dgdm_spatial_attention_work_bytes(...) bytes.
  * precise: 1 = product path, 3-term split-fp16 products (~fp32 accuracy): the tcgen05/TMEM kernel when D == 128 and heads == 8
  *             (DGDM-Base), else the mma.sync kernel; 2 = force the 3-term mma.sync kernel (comparison baseline);
- *          0 = single-pass fp16 operands on mma.sync (~1e-3, comparison only). head_dim must be 16. */
+ *          0 = single-pass fp16 operands on mma.sync (~1e-3, comparison only); 3 = force the exact fp32 CUDA-core kernel.
+ * head_dim 16 runs on the tensor cores; head_dim 4/8/32/64 (DGDM-Large: 16 heads x 8) run on the exact fp32 CUDA-core kernel. */
 size_t dgdm_spatial_attention_work_bytes(int Nq, int Nkv, int D, int heads, int num_seg);
 int dgdm_spatial_attention(const float* q_qkv, int ld_q, const float* q_pos, const int* qseg_ptr, int Nq,
                            const float* kv_qkv, int ld_kv, const float* kv_pos, const int* kseg_ptr, int Nkv,

@@ -169,6 +169,25 @@ def test_spatial_attention_core_vs_dense(precise, tol):
     assert rel_err(w, wref)[0] < 1e-5
 
 
+@pytest.mark.parametrize("D,H,precise", [(128, 16, None), (64, 2, None), (32, 8, None), (128, 8, 3)])
+def test_spatial_attention_other_head_dims_exact_fp32_kernel(D, H, precise):
+    """head_dim 8 (DGDM-Large: 16 heads over 128), 32, 4 — and head_dim 16 forced onto the same CUDA-core kernel (precise=3):
+    exact fp32 path vs a dense float64 softmax, ragged segments incl. a key tile tail (not a multiple of 64)."""
+    g = _gen(D + H)
+    segs = [0, 70, 70, 500]; n, hd = 500, D // H
+    qkv = torch.randn(n, 3 * D, generator=g); pos = torch.rand(n, 2, generator=g)
+    refs = []
+    for a, b in zip(segs[:-1], segs[1:]):
+        if b == a:
+            continue
+        q, k, v = (qkv[a:b, i * D:(i + 1) * D].double().view(b - a, H, hd).transpose(0, 1) for i in range(3))
+        w = torch.softmax(q @ k.transpose(1, 2) / hd ** 0.5 - torch.cdist(pos[a:b].double(), pos[a:b].double()) / 0.7, dim=-1)
+        refs.append((w @ v).transpose(0, 1).reshape(b - a, D))
+    seg = torch.tensor(segs, dtype=torch.int32, device=DEV)
+    out = ops.spatial_attention(qkv.to(DEV), pos.to(DEV), seg, 3, H, 0.7, precise=precise)
+    assert rel_err(out, torch.cat(refs))[0] < 3e-6
+
+
 def test_spatial_attention_large_scores_trigger_rescale():
     g = _gen(10)
     n, D, H = 700, 128, 8

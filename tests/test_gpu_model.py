@@ -153,3 +153,15 @@ def test_node_partitioned_forward_matches_single_gpu(world, n):
     for o in outs:
         assert rel_err(o["graph_embedding"], ref["graph_embedding"])[0] < 2e-5
         assert rel_err(o["classification_probs"], ref["classification_probs"])[0] < 2e-5
+
+
+def test_large_config_forward_vs_oracle():
+    """BASELINE.json configs[3] model (configs/dgdm_large.yaml:9-23: 1024-d nodes, hidden [768,512,256,128], 16 heads -> head_dim 8,
+    6 encoder layers -> patch P1, 768-wide rows -> column-grouped GEMM + stand-alone epilogue) on a small graph vs the oracle."""
+    cfg = dict(node_features=1024, hidden_dims=[768, 512, 256, 128], num_diffusion_steps=20, attention_heads=16, graph_layers=6)
+    m = make_model(cfg)
+    d = synth.tile_graph(600, 1024, seed=3)
+    ref = O.dgdm_forward(sd_cpu(m), oracle_cfg(cfg), d.x, d.edge_index, None, None, d.pos)
+    out = m.to(DEV)(d.to(DEV), return_embeddings=True)
+    assert rel_err(out["node_embeddings"], ref["node_embeddings"])[0] < 1e-4
+    assert rel_err(out["graph_embedding"], ref["graph_embedding"])[0] < 1e-4

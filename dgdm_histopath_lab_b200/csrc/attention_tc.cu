@@ -64,6 +64,29 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
   unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
 }
 __device__ __forceinline__ float tc_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// 2^x on the FMA / integer pipes (no MUFU): round-to-nearest split x = n + f with the 1.5*2^23 magic constant, degree-5
+// minimax polynomial for 2^f on [-0.5, 0.5] (max rel. error 2.1e-7, the class of ex2.approx), exponent inserted with one
+// integer multiply-add. Packed: two elements per call. Inputs are clamped at -125 (results below 2^-125 flush towards 0).
+__device__ __forceinline__ unsigned long long tc_ex2_poly2(unsigned long long x) {
+  const float x0 = fmaxf(lo32(x), -125.0f), x1 = fmaxf(hi32(x), -125.0f);
+  const unsigned long long xc = pk2(x0, x1);
+  const unsigned long long magic = pk2(12582912.0f, 12582912.0f);
+  const unsigned long long t = add2(xc, magic);
+  const unsigned long long f = sub2(xc, sub2(t, magic));
+  unsigned long long q = fma2(pk2(0.0013276466634124517f, 0.0013276466634124517f), f, pk2(0.009675540961325169f, 0.009675540961325169f));
+  q = fma2(q, f, pk2(0.05550713464617729f, 0.05550713464617729f));
+  q = fma2(q, f, pk2(0.24022120237350464f, 0.24022120237350464f));
+  q = fma2(q, f, pk2(0.6931469440460205f, 0.6931469440460205f));
+  q = fma2(q, f, pk2(1.0000001192092896f, 1.0000001192092896f));
+  const uint32_t r0 = (uint32_t)q + ((uint32_t)t << 23), r1 = (uint32_t)(q >> 32) + ((uint32_t)(t >> 32) << 23);
+  return (unsigned long long)r0 | ((unsigned long long)r1 << 32);
+}
+#ifndef TC_POLY_EVERY
+// Every TC_POLY_EVERY-th element pair takes the polynomial path (0 = never). MEASURED on B200 at 100k nodes (tools/attn_exp.sh):
+// 0 -> 35.2 ms, 4 -> 38.5 ms, 3 -> 38.9 ms, 2 -> 43.9 ms: the softmax warps are issue/latency-bound (2 warps per scheduler,
+// 216 registers each), so trading one MUFU op for ~6 FMA/ALU issue slots loses; the default therefore stays 0.
+#define TC_POLY_EVERY 0
+#endif
 __device__ __forceinline__ float tc_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ uint32_t tc_pack_h2(float a, float b) {       // a -> low half, b -> high half
   uint32_t r; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a)); return r;
@@ -262,8 +285,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc_kernel(const At
         for (int t = 0; t < 8; ++t) {
           const int e = 16 * ks + 2 * t;                              // element pair (e, e+1) of this 32-key chunk
           const unsigned long long x = add2(add2(pk2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), nbc[8 * ks + t]), nmu2);
-          const float p0 = tc_ex2(lo32(x)), p1 = tc_ex2(hi32(x));
-          const unsigned long long pp = pk2(p0, p1);
+          float p0, p1;
+          unsigned long long pp;
+          if (TC_POLY_EVERY > 0 && (t % (TC_POLY_EVERY > 0 ? TC_POLY_EVERY : 1)) == (TC_POLY_EVERY > 0 ? TC_POLY_EVERY - 1 : 0)) {
+            pp = tc_ex2_poly2(x); p0 = lo32(pp); p1 = hi32(pp);
+          } else {
+            p0 = tc_ex2(lo32(x)); p1 = tc_ex2(hi32(x)); pp = pk2(p0, p1);
+          }
           ls = add2(ls, pp);
           const float h0 = __uint_as_float(__float_as_uint(p0) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(p1) & 0xffffe000u);
           const unsigned long long ll = fma2(pk2(h0, h1), neg1, pp);  // p - hi, exact

@@ -467,6 +467,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc_kernel(const At
 
 static inline size_t tc_al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// Key splits per query tile. Two constraints: (1) occupancy — at least ~8 CTAs of work per SM; (2) ACCURACY — the tensor core
+// accumulates O in fp32 with truncation, 12 accumulate steps per key block (4 K-steps x 3 split terms), which biases a long
+// chain low by ~3.7e-8 per step (measured: -3.5e-4 at 781 blocks per CTA, tests/test_gpu_properties.py). The chain is capped
+// at TC_MAX_CHAIN key blocks per CTA (bias <= ~2e-5; 32 costs +1.1 ms at 100k nodes, 48 costs +0.5 ms); the partial (O, m, l) of the splits are merged in fp32 round-to-nearest
+// by attn_combine_kernel.
+constexpr int TC_MAX_CHAIN = 48;
 int attn_tc_nsplit(int Nq, int Nkv, int num_seg) {
   const int tiles = (Nq + TC_QT - 1) / TC_QT + num_seg;
   int s = (148 * 8 + tiles - 1) / tiles;                       // aim for >= ~8 CTAs of work per SM
@@ -474,6 +480,9 @@ int attn_tc_nsplit(int Nq, int Nkv, int num_seg) {
   const int max_s = avg_blocks / 8 > 1 ? avg_blocks / 8 : 1;   // at least ~8 key blocks per CTA
   if (s > max_s) s = max_s;
   if (s > 16) s = 16;
+  const int max_blocks = (Nkv + TC_BN - 1) / TC_BN;            // upper bound of any segment's block count
+  const int s_chain = (max_blocks + TC_MAX_CHAIN - 1) / TC_MAX_CHAIN;
+  if (s < s_chain) s = s_chain;
   if (s < 1) s = 1;
   return s;
 }

@@ -35,6 +35,24 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the newest committed `ncu --set full` summary under
+    profiles/ (captured at this workload on one GPU); (None, None) when no capture names the kernel."""
+    import glob
+    import re
+    best = (None, None)
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "attn_tc_*.txt"))):
+        txt = open(path).read()
+        if kernel not in txt:
+            continue
+        rd = re.search(r"dram__bytes_read\.sum\s+([0-9.]+)\s+(\w+)", txt)
+        wr = re.search(r"dram__bytes_write\.sum\s+([0-9.]+)\s+(\w+)", txt)
+        if rd and wr:
+            mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            best = (float(rd.group(1)) * mult.get(rd.group(2), 1.0) + float(wr.group(1)) * mult.get(wr.group(2), 1.0), os.path.relpath(path, ROOT))
+    return best
+
+
 class ClockSampler:
     def __init__(self, dev):
         self.dev, self.rows, self._stop, self._t = dev, [], threading.Event(), None
@@ -117,6 +135,8 @@ def main():
     ap.add_argument("--ref-nodes", type=int, default=2000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="graph100k", choices=["graph100k", "batch4x50k"],
+                    help="graph100k = BASELINE.json's metric (one 100k-node tile graph); batch4x50k = configs[1] (4 x 50k-node graphs in one Batch)")
     ap.add_argument("--no-fused-halo", action="store_true", help="multi-GPU: NCCL all-gather per propagate instead of the GEMM-epilogue P2P/multicast stores")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -143,8 +163,13 @@ def main():
         model = DGDMModel(**BASE_CFG).eval()
     model.load_state_dict(synth.seeded_state_dict(model, 0))
     model = model.to(dev)
-    host = synth.tile_graph(args.nodes, 768, seed=1234)
+    if args.workload == "batch4x50k":
+        from dgdm_histopath_lab_b200 import Batch
+        host = Batch.from_data_list([synth.tile_graph(args.nodes // 2, 768, seed=100 + i) for i in range(4)])
+    else:
+        host = synth.tile_graph(args.nodes, 768, seed=1234)
     N, E = host.x.size(0), host.edge_index.size(1)
+    host_batch = getattr(host, "batch", None)
     rows = None
     if world > 1:
         # 1-D node partition (parallel.py): every rank holds the graph structure and pos, and only its own rows of x
@@ -153,6 +178,8 @@ def main():
         b = even_bounds(N, world)
         rows = (b[rank], b[rank + 1])
         data = Data(x=host.x[rows[0]:rows[1]].to(dev), edge_index=host.edge_index.to(dev), pos=host.pos.to(dev), num_nodes=N)
+        if host_batch is not None:
+            data.batch = host_batch.to(dev)
     else:
         data = host.to(dev)
 
@@ -174,10 +201,8 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    th0 = time.perf_counter()
     for _ in range(args.steps):
         out = step_resident()
-    host_ms = 1e3 * (time.perf_counter() - th0) / args.steps      # CPU time to enqueue one forward (no device sync inside)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -196,6 +221,8 @@ def main():
     if not args.no_e2e:
         from dgdm_histopath_lab_b200.loader import DevicePrefetcher
         hg = Data(x=host.x.pin_memory(), edge_index=host.edge_index.pin_memory(), pos=host.pos.pin_memory())
+        if host_batch is not None:
+            hg.batch = host_batch.pin_memory()
         nx = N if rows is None else rows[1] - rows[0]
         h2d = nx * 768 * 4 + hg.edge_index.numel() * 8 + hg.pos.numel() * 4
 
@@ -244,6 +271,7 @@ def main():
         roof["mufu"] = {"achieved_gops": 1.25 * att_exp / (att_ms * 1e-3) / 1e9, "peak_gops": mufu_peak,
                         "frac": 1.25 * att_exp / (att_ms * 1e-3) / 1e9 / mufu_peak, "ops_per_score": 1.25}
     roof["frac"] = roof["achieved"] / roof["peak"] if roof["achieved"] else None
+    roof["traffic"], roof["traffic_source"] = ncu_traffic("spatial_attn_tc_kernel")
     roof_hbm = {"kernel": "spmm_gcn_kernel (all launches)", "bound": "hbm", "achieved": spmm_bytes / (spmm_ms * 1e-3) / 1e9 if spmm_ms else None,
                 "peak": pk["hbm"], "unit": "GB/s", "traffic": None, "ms": spmm_ms, "launches": len(meta.get("spmm", [])),
                 "algorithmic_bytes": spmm_bytes}
@@ -262,14 +290,16 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": f"DGDM-Base forward (eval, inference mode, return_embeddings) on one synthetic {N}-node 768-d tile graph, "
-                                       f"E={E} directed edges, random-init seeded weights", "nodes": N, "edges": E,
+                "config": {"workload": (f"DGDM-Base forward (eval, inference mode, return_embeddings) on one synthetic {N}-node 768-d tile graph, "
+                                        f"E={E} directed edges, random-init seeded weights") if args.workload == "graph100k" else
+                                       (f"DGDM-Base forward on a Batch of 4 synthetic {N // 4}-node 768-d tile graphs (configs[1]), E={E} directed edges"),
+                           "nodes": N, "edges": E,
                            "l2_policy": "inputs larger than L2 (x = 307 MB, activations > 200 MB per layer)",
                            "parallelism": "single GPU" if world == 1 else f"1-D node partition over {world} GPUs: features row-partitioned, NCCL all-gather "
                                           f"of projected rows per propagate (halo), context-parallel attention, replicated graph structure",
                            "attention_precise": ops.attention_precise_default(), "gemm": ops.gemm_mode(),
                            "halo": None if world == 1 else type(model._comm).__name__ + ("/multicast" if getattr(model._comm, "multicast", False) else "")},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms, "roofline": roof, "roofline_hbm": roof_hbm, "roofline_gemm": roof_gemm,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "roofline_hbm": roof_hbm, "roofline_gemm": roof_gemm,
                 "cpu_baseline": cpu, "per_call_ms": {k: round(v[1], 4) for k, v in prof.items()},
                 "graph_embedding_checksum": float(out["graph_embedding"].double().abs().sum().item())}
         print(json.dumps(line), flush=True)

@@ -16,16 +16,29 @@ class DevicePrefetcher:
         """rows: optional (a, b) — copy only these rows of x (the rows a rank owns in node-partitioned execution)."""
         self.graphs, self.device, self.rows = graphs, torch.device(device), rows
         self.stream = torch.cuda.Stream(device=self.device)
+        self._slots = [{}, {}]          # two sets of device staging tensors, reused (no allocator traffic in the loop)
+        self._n = 0
+
+    def _buf(self, slot, key, host):
+        t = slot.get(key)
+        if t is None or t.shape != host.shape or t.dtype != host.dtype:
+            t = torch.empty(host.shape, dtype=host.dtype, device=self.device)
+            slot[key] = t
+        return t
 
     def _stage(self, g):
+        slot = self._slots[self._n & 1]
+        self._n += 1
+        # the slot was last used two graphs ago: everything enqueued on the consumer's stream so far includes that forward
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.stream):
             x = g.x if self.rows is None else g.x[self.rows[0]:self.rows[1]]
             kw = {}
             for k in ("edge_index", "edge_attr", "pos", "batch"):
                 v = getattr(g, k, None)
-                kw[k] = None if v is None else v.to(self.device, non_blocking=True)
+                kw[k] = None if v is None else self._buf(slot, k, v).copy_(v, non_blocking=True)
             batch = kw.pop("batch")
-            d = Data(x=x.to(self.device, non_blocking=True), **kw)
+            d = Data(x=self._buf(slot, "x", x).copy_(x, non_blocking=True), **kw)
             if batch is not None:
                 d.batch = batch
             if self.rows is not None:
@@ -42,11 +55,7 @@ class DevicePrefetcher:
             return
         while nxt is not None:
             d, ev = nxt
-            cur = torch.cuda.current_stream(self.device)
-            cur.wait_event(ev)
-            for v in d.__dict__.values():
-                if torch.is_tensor(v):
-                    v.record_stream(cur)
+            torch.cuda.current_stream(self.device).wait_event(ev)
             try:
                 nxt = self._stage(next(it))          # overlaps with the consumer's forward on graph `d`
             except StopIteration:

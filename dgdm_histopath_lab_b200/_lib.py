@@ -68,6 +68,11 @@ SIGNATURES = {
     "dgdm_knn_cosine_work_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "dgdm_knn_cosine": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                 c_void_p]),
+    "dgdm_row_sqnorm_f64": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "dgdm_knn_cosine_tc_work_bytes": (c_size_t, [c_int]),
+    "dgdm_knn_cosine_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_size_t, c_void_p]),
+    "dgdm_gemm_f16x2_strided": (c_int, [C.POINTER(GemmParams), C.c_longlong, c_void_p]),
     "dgdm_knn2d": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -6,6 +6,7 @@ filtering, duplicate removal and edge emission reproduce the reference's order e
 """
 import ctypes as C
 import logging
+import math
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -58,11 +59,27 @@ class GraphEdge:
     features: Optional[np.ndarray] = None
 
 
-def knn_cosine(features, k, q0=0, nq=None, chunk=None):
-    """features: float32 CUDA [n,d]. Returns (idx int32 [nq,k], cos float32 [nq,k], dist float64 [nq,k]) for rows q0..q0+nq."""
-    lib = _lib.load()
+TC_MIN_ROWS = 4096          # below this the exact fp64 CUDA-core path is used directly
+KNN_STATS = {"rows": 0, "flagged": 0}
+
+
+def knn_cosine(features, k, q0=0, nq=None, chunk=None, mode=None):
+    """features: float32 CUDA [n,d]. Returns (idx int32 [nq,k], cos float32 [nq,k], dist float64 [nq,k]) for rows q0..q0+nq
+    (q0/nq = the query rows one rank owns when the rows are sharded across GPUs).
+    mode 'exact': fp64 Gram on CUDA cores. mode 'tc' (default for n >= TC_MIN_ROWS): tcgen05 candidate pass + exact fp64
+    re-rank + exact recomputation of the rows whose top-k could not be proved (KNN_STATS counts them); same results."""
     n, d = features.shape
     nq = n - q0 if nq is None else nq
+    if mode is None:
+        mode = "tc" if (n >= TC_MIN_ROWS and d % 4 == 0 and k <= 32) else "exact"
+    if mode == "tc":
+        return _knn_cosine_tc(features, k, q0, nq, chunk)
+    return _knn_cosine_exact(features, k, q0, nq, chunk)
+
+
+def _knn_cosine_exact(features, k, q0, nq, chunk=None):
+    lib = _lib.load()
+    n, d = features.shape
     dev = features.device
     idx = torch.empty(nq, k, dtype=torch.int32, device=dev)
     cos = torch.empty(nq, k, dtype=torch.float32, device=dev)
@@ -75,6 +92,44 @@ def knn_cosine(features, k, q0=0, nq=None, chunk=None):
         work = torch.empty(wb, dtype=torch.uint8, device=dev)
         _check(lib.dgdm_knn_cosine(_p(features), n, d, q0 + c0, cn, k, _p(idx[c0:]), _p(cos[c0:]), _p(dist[c0:]), _p(work), wb,
                                    _stream()), "dgdm_knn_cosine")
+    return idx, cos, dist
+
+
+def _knn_cosine_tc(features, k, q0, nq, chunk=None):
+    from . import ops
+    lib = _lib.load()
+    n, d = features.shape
+    dev = features.device
+    # power-of-two prescale so that the fp16 hi/lo planes of the largest entries sit well inside the normal fp16 range; it is
+    # exact in fp32/fp64, so rankings, ties and cosines are unchanged and distances are rescaled exactly at the end
+    amax = float(features.abs().max().item())
+    scale = 2.0 ** round(math.log2(8.0 / amax)) if amax > 0 else 1.0
+    n_pad = (n + 15) // 16 * 16
+    fs = torch.zeros(n_pad, d, dtype=torch.float32, device=dev)
+    torch.mul(features, scale, out=fs[:n])
+    img = ops.SplitWeight(fs)
+    sq = torch.empty(n_pad, dtype=torch.float64, device=dev)
+    _check(lib.dgdm_row_sqnorm_f64(_p(fs), n_pad, d, _p(sq), _stream()), "dgdm_row_sqnorm_f64")
+    idx = torch.empty(nq, k, dtype=torch.int32, device=dev)
+    cos = torch.empty(nq, k, dtype=torch.float32, device=dev)
+    dist = torch.empty(nq, k, dtype=torch.float64, device=dev)
+    flags = torch.empty(nq, dtype=torch.int32, device=dev)
+    chunk = 16384 if chunk is None else chunk
+    wb = int(lib.dgdm_knn_cosine_tc_work_bytes(min(chunk, nq)))
+    work = torch.empty(wb, dtype=torch.uint8, device=dev)
+    for c0 in range(0, nq, chunk):
+        cn = min(chunk, nq - c0)
+        _check(lib.dgdm_knn_cosine_tc(_p(fs), img.hi_ptr, _p(sq), n, n_pad, d, q0 + c0, cn, k, _p(idx[c0:]), _p(cos[c0:]), _p(dist[c0:]),
+                                      _p(flags[c0:]), _p(work), wb, _stream()), "dgdm_knn_cosine_tc")
+    bad = torch.nonzero(flags).reshape(-1).tolist()
+    KNN_STATS["rows"] += nq
+    KNN_STATS["flagged"] += len(bad)
+    if bad:       # rows whose top-k could not be proved from 32 candidates: exact fp64 path, one row at a time
+        fv = fs[:n]
+        for r in bad:
+            i1, c1, d1 = _knn_cosine_exact(fv, k, q0 + r, 1)
+            idx[r], cos[r], dist[r] = i1[0], c1[0], d1[0]
+    dist /= scale
     return idx, cos, dist
 
 

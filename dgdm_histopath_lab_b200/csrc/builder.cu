@@ -138,6 +138,114 @@ __global__ void __launch_bounds__(256) pair_cosine_kernel(const float* __restric
   if (lane == 0) cosv[w] = (float)acc;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Tensor-core candidate pass (config 3: 1M x 768 rows). The N^2 x 768 Gram work runs on tcgen05 through dgdm_gemm_f16x2
+// (3-term split-fp16 products, fp32 accumulate: |error| <~ 1e-5 |x||y|), 512 key columns at a time; per query row a sorted
+// list of the KC = 32 nearest candidates by APPROXIMATE distance is maintained across the column groups; the candidates are
+// then re-ranked with sklearn's exact fp64 arithmetic. A row is flagged when exactness cannot be PROVED, i.e. unless
+//     (approximate distance of the worst kept candidate) - eps  >  (exact distance of the k-th neighbour),
+// in which case some non-candidate could still belong to the true top-k; the caller recomputes flagged rows with the exact
+// fp64 path (dgdm_knn_cosine). Results are therefore always exactly the reference's.
+constexpr int KNN_KC = 32;
+
+__global__ void knn_cand_init_kernel(float* __restrict__ cd, int* __restrict__ ci, size_t total) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) { cd[i] = INFINITY; ci[i] = 0x7fffffff; }
+}
+
+// warp per query row; lane l holds the l-th smallest (distance, index) so far. G [nq, ncols] = approximate dot products.
+__global__ void __launch_bounds__(256) knn_cand_merge_kernel(const float* __restrict__ G, int ldg, int nq, int ncols, int g0, int n,
+                                                             int q0, const double* __restrict__ sq, float* __restrict__ cd,
+                                                             int* __restrict__ ci) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= nq) return;
+  float ld = cd[(size_t)row * KNN_KC + lane];
+  int li = ci[(size_t)row * KNN_KC + lane];
+  float thr = __shfl_sync(0xffffffffu, ld, 31);
+  const double sqq = sq[q0 + row];
+  const float* g = G + (size_t)row * ldg;
+  for (int c = 0; c < ncols; c += 32) {
+    const int j = g0 + c + lane;
+    float v = INFINITY;
+    if (c + lane < ncols && j < n) {
+      const double d2 = sqq + sq[j] - 2.0 * (double)g[c + lane];
+      v = d2 > 0.0 ? (float)d2 : 0.f;
+    }
+    unsigned mask = __ballot_sync(0xffffffffu, v < thr);
+    while (mask) {
+      const int b = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const float vb = __shfl_sync(0xffffffffu, v, b);
+      const int jb = g0 + c + b;
+      if (!(vb < thr)) continue;                                  // the threshold moved since the ballot
+      const int pos = __popc(__ballot_sync(0xffffffffu, ld <= vb));   // entries that stay in front of the new one
+      const float up_d = __shfl_up_sync(0xffffffffu, ld, 1);
+      const int up_i = __shfl_up_sync(0xffffffffu, li, 1);
+      if (lane > pos) { ld = up_d; li = up_i; }
+      else if (lane == pos) { ld = vb; li = jb; }
+      thr = __shfl_sync(0xffffffffu, ld, 31);
+    }
+  }
+  cd[(size_t)row * KNN_KC + lane] = ld;
+  ci[(size_t)row * KNN_KC + lane] = li;
+}
+
+// warp per query row: exact fp64 squared distances of the 32 candidates (sklearn: |x|^2 - 2 x.y + |y|^2, clipped at 0), sorted by
+// (distance, index); the first k are written; flag = 1 unless exactness is proved (see above).
+__global__ void __launch_bounds__(128) knn_rerank_kernel(const float* __restrict__ F, int n, int d, int q0, int nq, int k,
+                                                         const double* __restrict__ sq, const double* __restrict__ sq_max_ptr, const float* __restrict__ cd,
+                                                         const int* __restrict__ ci, int* __restrict__ idx_out,
+                                                         double* __restrict__ dist_out, int* __restrict__ flags) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= nq) return;
+  const int my_i = ci[(size_t)row * KNN_KC + lane];
+  const float worst_approx = __shfl_sync(0xffffffffu, cd[(size_t)row * KNN_KC + lane], 31);
+  const float* xq = F + (size_t)(q0 + row) * d;
+  double my_d = INFINITY;
+  for (int c = 0; c < KNN_KC; ++c) {
+    const int j = __shfl_sync(0xffffffffu, my_i, c);
+    if (j == 0x7fffffff) continue;                                 // fewer than 32 rows exist
+    const float* xj = F + (size_t)j * d;
+    double acc = 0.0;
+    for (int t = lane; t < d; t += 32) acc = fma((double)xq[t], (double)xj[t], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const double d2 = sq[q0 + row] + (-2.0 * acc) + sq[j];
+    if (lane == c) my_d = d2 > 0.0 ? d2 : 0.0;
+  }
+  // rank of each candidate among the 32 by (distance, index): O(32) compares per lane
+  int rank = 0;
+  for (int c = 0; c < KNN_KC; ++c) {
+    const double od = __shfl_sync(0xffffffffu, my_d, c);
+    const int oi = __shfl_sync(0xffffffffu, my_i, c);
+    if (c != lane && knn_less(od, oi, my_d, my_i)) ++rank;
+  }
+  if (rank < k && my_i != 0x7fffffff) { idx_out[(size_t)row * k + rank] = my_i; dist_out[(size_t)row * k + rank] = sqrt(my_d); }
+  // exactness proof
+  double kth = 0.0;
+  {
+    const unsigned who = __ballot_sync(0xffffffffu, rank == k - 1);
+    const int src = who ? __ffs(who) - 1 : 0;
+    kth = __shfl_sync(0xffffffffu, my_d, src);
+  }
+  if (lane == 0) {
+    const double eps = 4e-5 * fmax(sq[q0 + row], *sq_max_ptr) + 1e-30;
+    const bool all_seen = n <= KNN_KC;
+    flags[row] = (all_seen || (double)worst_approx - eps > kth) ? 0 : 1;
+  }
+}
+
+__global__ void max_f64_kernel(const double* __restrict__ v, int n, double* __restrict__ out) {
+  __shared__ double red[32];
+  double m = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, v[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) { for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmax(m, red[i]); *out = m; }
+}
+
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static int launch_topk(const double* D2, int n, int nq, int k, int* idx, double* dist, cudaStream_t s) {
@@ -183,6 +291,55 @@ extern "C" int dgdm_knn_cosine(const float* F, int n, int d, int q0, int nq, int
   gram_dist_kernel<<<grid, 256, 0, s>>>(F, n, d, q0, nq, sq, D2);
   int rc = launch_topk(D2, n, nq, k, nbr_idx, nbr_dist, s);
   if (rc != DGDM_OK) return rc;
+  const long long warps = (long long)nq * k;
+  pair_cosine_kernel<<<(int)((warps + 7) / 8), 256, 0, s>>>(F, d, q0, nq, k, nbr_idx, sq, nbr_cos);
+  DGDM_CHECK_LAUNCH();
+  return DGDM_OK;
+}
+
+extern "C" int dgdm_gemm_f16x2_strided(const dgdm_gemm_params* p, long long w_plane_stride_bytes, void* stream);
+
+extern "C" int dgdm_row_sqnorm_f64(const float* F, int n, int d, double* sq, void* stream) {
+  if (!F || !sq || n <= 0 || d <= 0) return DGDM_ERR_INVALID;
+  row_sqnorm_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(F, n, d, sq);
+  DGDM_CHECK_LAUNCH();
+  return DGDM_OK;
+}
+
+constexpr int KNN_TC_GROUP = 512;
+extern "C" size_t dgdm_knn_cosine_tc_work_bytes(int nq) {
+  return al256((size_t)nq * KNN_TC_GROUP * 4) + 2 * al256((size_t)nq * KNN_KC * 4) + 512;
+}
+
+// F: [n_pad, d] fp32 with n_pad = round_up(n, 16) (pad rows zero), W_img = dgdm_split_weight_f16 images of the same matrix
+// (n_pad rows), sq = fp64 squared row norms [n_pad]. d % 4 == 0. Query rows [q0, q0+nq). k <= 32 neighbours per row incl. the row
+// itself. row_flags[nq]: 0 = provably exact, 1 = recompute this row with dgdm_knn_cosine.
+extern "C" int dgdm_knn_cosine_tc(const float* F, const void* W_img, const double* sq, int n, int n_pad, int d, int q0, int nq, int k,
+                                  int* nbr_idx, float* nbr_cos, double* nbr_dist, int* row_flags, void* work, size_t work_bytes,
+                                  void* stream) {
+  if (!F || !W_img || !sq || !nbr_idx || !nbr_cos || !nbr_dist || !row_flags || !work) return DGDM_ERR_INVALID;
+  if (n <= 0 || n_pad < n || (n_pad % 16) != 0 || d <= 0 || (d % 4) != 0 || k <= 0 || k > KNN_KC || k > n) return DGDM_ERR_INVALID;
+  if (q0 < 0 || nq <= 0 || q0 + nq > n || work_bytes < dgdm_knn_cosine_tc_work_bytes(nq)) return DGDM_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  uint8_t* w = (uint8_t*)(((uintptr_t)work + 255) & ~(uintptr_t)255);
+  float* G = (float*)w; w += al256((size_t)nq * KNN_TC_GROUP * 4);
+  float* cd = (float*)w; w += al256((size_t)nq * KNN_KC * 4);
+  int* ci = (int*)w; w += al256((size_t)nq * KNN_KC * 4);
+  double* sq_max = (double*)w;
+  knn_cand_init_kernel<<<148 * 4, 256, 0, s>>>(cd, ci, (size_t)nq * KNN_KC);
+  max_f64_kernel<<<1, 1024, 0, s>>>(sq, n, sq_max);
+  const int kpad = (d + 63) / 64 * 64;
+  for (int g0 = 0; g0 < n_pad; g0 += KNN_TC_GROUP) {
+    const int nc = (n_pad - g0) < KNN_TC_GROUP ? (n_pad - g0) : KNN_TC_GROUP;
+    dgdm_gemm_params p = {};
+    p.A = F + (size_t)q0 * d; p.lda = d; p.M = nq; p.K = d;
+    p.W_hi = (const uint8_t*)W_img + (size_t)g0 * 128; p.W_lo = (const uint8_t*)p.W_hi + (size_t)n_pad * 128; p.ldw = kpad;
+    p.N = nc; p.C = G; p.ldc = KNN_TC_GROUP; p.a_scale = 1.0f; p.ln_eps = 1e-5f;
+    const int rc = dgdm_gemm_f16x2_strided(&p, (long long)n_pad * 128, stream);
+    if (rc != DGDM_OK) return rc;
+    knn_cand_merge_kernel<<<(nq + 7) / 8, 256, 0, s>>>(G, KNN_TC_GROUP, nq, nc, g0, n, q0, sq, cd, ci);
+  }
+  knn_rerank_kernel<<<(nq + 3) / 4, 128, 0, s>>>(F, n, d, q0, nq, k, sq, sq_max, cd, ci, nbr_idx, nbr_dist, row_flags);
   const long long warps = (long long)nq * k;
   pair_cosine_kernel<<<(int)((warps + 7) / 8), 256, 0, s>>>(F, d, q0, nq, k, nbr_idx, sq, nbr_cos);
   DGDM_CHECK_LAUNCH();

@@ -545,6 +545,17 @@ extern "C" int dgdm_gemm_f16x2(const dgdm_gemm_params* p, void* stream) {
   return dgdm_rowwise_epilogue(p->C, p->ldc, p->M, p->N, &ep, stream);
 }
 
+// Same kernel on a row sub-range [row0, row0 + p->N) of a larger weight image (p->N <= 512): W_hi points at row0 of the hi plane
+// of K-block 0 and w_plane_stride_bytes = (rows of the whole image) * 128. Used by the Gram-matrix candidate pass of the edge builder.
+extern "C" int dgdm_gemm_f16x2_strided(const dgdm_gemm_params* p, long long w_plane_stride_bytes, void* stream) {
+  if (!p || !p->A || !p->W_hi || !p->C) return DGDM_ERR_INVALID;
+  if (p->N < 16 || p->N > 512 || (p->N % 16) != 0 || w_plane_stride_bytes < (long long)p->N * 128) return DGDM_ERR_INVALID;
+  if (p->K < 4 || (p->K % 4) != 0 || (p->lda % 4) != 0 || (p->ldw % 64) != 0 || p->ldw < p->K || (p->ldc % 4) != 0) return DGDM_ERR_INVALID;
+  if (!(p->a_scale > 0.f) || p->n_peers != 0) return DGDM_ERR_INVALID;
+  if (p->M <= 0) return DGDM_OK;
+  return launch_gemm(*p, w_plane_stride_bytes, (cudaStream_t)stream);
+}
+
 extern "C" int dgdm_split_weight_f16(const float* W, int N, int K, void* W_hi, void* W_lo, int Kpad, void* stream) {
   if (!W || !W_hi || !W_lo || N <= 0 || (N % 8) != 0 || K <= 0 || Kpad < K || (Kpad % 64) != 0) return DGDM_ERR_INVALID;
   if ((uint8_t*)W_lo != (uint8_t*)W_hi + (size_t)N * 128) return DGDM_ERR_INVALID;

@@ -22,6 +22,7 @@ KERNELS_PER_CALL = {
     "dgdm_unpool_add_act": 1, "dgdm_segment_softmax_scores": 1, "dgdm_segment_minmax": 1, "dgdm_spatial_pe_add": 1,
     "dgdm_spatial_attention": 6, "dgdm_spatial_attention_weights": 1, "dgdm_attention_pool": 2, "dgdm_diffusion_add_noise": 1,
     "dgdm_groupnorm_silu": 1, "dgdm_ddpm_update": 1, "dgdm_validate_inputs": 1, "dgdm_knn_cosine": 4, "dgdm_knn2d": 2,
+    "dgdm_row_sqnorm_f64": 1, "dgdm_knn_cosine_tc": 6,
 }
 LAUNCHES = {"kernels": 0, "calls": 0}
 _PROFILE = None      # when set to a list: (name, start_event, end_event) per C call (bench.py's per-kernel timing pass)

@@ -195,6 +195,19 @@ int dgdm_validate_inputs(const float* x, size_t n_x, const int64_t* edge_index, 
 size_t dgdm_knn_cosine_work_bytes(int nq, int n, int d, int k);
 int dgdm_knn_cosine(const float* F, int n, int d, int q0, int nq, int k, int* nbr_idx, float* nbr_cos,
                     double* nbr_dist, void* work, size_t work_bytes, void* stream);
+/* Tensor-core candidate pass for large n (BASELINE.json configs[2]: 1M x 768 rows, query rows sharded across GPUs by q0/nq): the
+ * N^2 x d Gram work runs on tcgen05 through the split-fp16 GEMM, 512 key columns at a time; per query row the 32 nearest
+ * candidates by approximate distance are kept, re-ranked with the exact fp64 arithmetic above, and a row is flagged
+ * (row_flags[i] = 1) unless it is PROVED that no non-candidate can belong to its top-k — the caller recomputes flagged rows
+ * with dgdm_knn_cosine, so results are always exactly the reference's. F: [n_pad, d] (n_pad = round_up(n,16), pad rows zero,
+ * d % 4 == 0), W_img: dgdm_split_weight_f16 images of the same matrix, sq: dgdm_row_sqnorm_f64 of it. k <= 32. */
+int dgdm_row_sqnorm_f64(const float* F, int n, int d, double* sq, void* stream);
+size_t dgdm_knn_cosine_tc_work_bytes(int nq);
+int dgdm_knn_cosine_tc(const float* F, const void* W_img, const double* sq, int n, int n_pad, int d, int q0, int nq, int k,
+                       int* nbr_idx, float* nbr_cos, double* nbr_dist, int* row_flags, void* work, size_t work_bytes, void* stream);
+/* dgdm_gemm_f16x2 on a row sub-range of a larger weight image: W_hi points at the first row of the range in the hi plane of
+ * K-block 0, w_plane_stride_bytes = (rows of the whole image) * 128; p->N <= 512; plain product (no epilogue fields needed). */
+int dgdm_gemm_f16x2_strided(const dgdm_gemm_params* p, long long w_plane_stride_bytes, void* stream);
 /* _create_spatial_edges (:290-320): exact k nearest neighbours on 2-D fp64 coords (query row included, callers pass
  * spatial_k+1), ascending distance, ties towards the lower index. */
 int dgdm_knn2d(const double* coords, int n, int q0, int nq, int k, int* nbr_idx, double* nbr_dist, void* stream);

@@ -165,3 +165,40 @@ def test_large_config_forward_vs_oracle():
     out = m.to(DEV)(d.to(DEV), return_embeddings=True)
     assert rel_err(out["node_embeddings"], ref["node_embeddings"])[0] < 1e-4
     assert rel_err(out["graph_embedding"], ref["graph_embedding"])[0] < 1e-4
+
+
+def test_builder_tensor_core_candidate_path_is_exact():
+    """dgdm_knn_cosine_tc (tcgen05 Gram candidates -> exact fp64 re-rank -> proved or recomputed) against the exact fp64 CUDA-core
+    path on config-3-like data (768-d clustered features whose within-cluster cosine straddles the 0.7 threshold), incl. a row
+    count that is not a multiple of 16 / 512, row-sharded query ranges (q0/nq), and the reference golden edge list."""
+    from dgdm_histopath_lab_b200 import PatchInfo, SlideData, TissueGraphBuilder, builder
+    n, d, k = 5003, 768, 17
+    f = torch.as_tensor(synth.clustered_features(n, d=d, num_clusters=40, seed=3)).float().to(DEV)
+    builder.KNN_STATS.update(rows=0, flagged=0)
+    i_e, c_e, d_e = builder.knn_cosine(f, k, mode="exact")
+    i_t, c_t, d_t = builder.knn_cosine(f, k, mode="tc")
+    assert torch.equal(i_t, i_e), "neighbour lists (indices and order) must be identical"
+    assert torch.equal(c_t, c_e)
+    assert (d_t[:, 1:] - d_e[:, 1:]).abs().max().item() < 1e-12 and d_t[:, 0].abs().max().item() < 1e-6   # column 0 = the row itself (cancellation noise)
+    assert builder.KNN_STATS["flagged"] < 0.02 * n, builder.KNN_STATS      # the proof succeeds for almost every row
+    # a rank's shard of the query rows
+    i_s, c_s, _ = builder.knn_cosine(f, k, q0=1237, nq=900, mode="tc")
+    assert torch.equal(i_s, i_e[1237:2137]) and torch.equal(c_s, c_e[1237:2137])
+    # uniform random rows (distances concentrate): exactness must still hold through the flag-and-recompute path
+    g = torch.Generator().manual_seed(5)
+    u = torch.randn(4100, 64, generator=g).to(DEV)
+    iu_e, _, _ = builder.knn_cosine(u, k, mode="exact")
+    iu_t, _, _ = builder.knn_cosine(u, k, mode="tc")
+    assert torch.equal(iu_t, iu_e)
+    # and the reference golden through build_graph with the tensor-core path forced
+    gld = golden("builder_600.npz")
+    feats = synth.clustered_features(600, d=64, num_clusters=12, seed=21, sigma_lo=0.05, sigma_hi=0.11)
+    xs, ys, dims = synth.jittered_grid_coords(600, seed=21, extent=3000)
+    patches = [PatchInfo(int(xs[i]), int(ys[i]), 0, 20.0, f"s_patch_{i:06d}", 0.9, feats[i]) for i in range(600)]
+    old = builder.TC_MIN_ROWS
+    builder.TC_MIN_ROWS = 1
+    try:
+        gph = TissueGraphBuilder(feature_extractor="none").build_graph(SlideData("s", patches, {"dimensions": dims}))
+    finally:
+        builder.TC_MIN_ROWS = old
+    assert np.array_equal(gph.edge_index.numpy(), gld["edge_index"])

@@ -249,6 +249,14 @@ def test_diffusion_forward_and_sample_vs_golden_and_oracle():
     s = m.diffusion_layer.sample((40, 32), torch.device(DEV), num_inference_steps=6, init=torch.tensor(g["sample_init"]),
                                  step_noise=torch.tensor(g["sample_steps"]))
     assert rel_err(s, g["sample_out"])[0] < 1e-4
+    # CUDA-graph replay (second call with the same shape) == eager loop, bit for bit; and with fresh inputs
+    dl = m.diffusion_layer
+    init2, noise2 = torch.randn(40, 32, generator=_gen(77)), torch.randn(5, 40, 32, generator=_gen(78))
+    eager = dl.sample((40, 32), torch.device(DEV), num_inference_steps=6, init=init2, step_noise=noise2, use_graph=False)
+    replay = dl.sample((40, 32), torch.device(DEV), num_inference_steps=6, init=init2, step_noise=noise2)
+    assert torch.equal(eager, replay) and len(dl._graphs) == 1
+    ref2 = O.diffusion_sample(sd_cpu(m), "diffusion_layer", O.diffusion_schedule(SMALL_CFG["num_diffusion_steps"], "cosine"), init2, noise2, 6)
+    assert rel_err(replay, ref2)[0] < 1e-4
 
 
 def test_compute_dynamic_edges_vs_golden():

@@ -4,7 +4,6 @@ The O(N^2) parts (768-d Gram / Euclidean kNN / cosine, 2-D kNN) run on the GPU t
 filtering, duplicate removal and edge emission reproduce the reference's order exactly with vectorised numpy
 (the reference uses Python loops over dataclass objects; the result — indices AND order — is the same).
 """
-import ctypes as C
 import logging
 import math
 from dataclasses import dataclass
@@ -276,6 +275,47 @@ class TissueGraphBuilder:
         data.num_patches = len(slide_data.patches)
         data.slide_metadata = slide_data.metadata
         return data
+
+    # ---------------------------------------------------------------------------------- hierarchy
+    def create_hierarchical_graph(self, base_graph, levels=3):
+        """preprocessing/tissue_graph_builder.py:449-471: [base, pooled, pooled of pooled, ...] with pool_ratio 0.5."""
+        graphs, cur = [base_graph], base_graph
+        for _ in range(1, levels):
+            cur = self._pool_graph(cur, pool_ratio=0.5)
+            graphs.append(cur)
+        return graphs
+
+    def _pool_graph(self, graph, pool_ratio=0.5):
+        """:473-516. Keep the max(1, int(ratio*N)) nodes of highest degree (occurrences in either row of edge_index), ascending
+        order, relabel and filter the edges (order kept). The reference computes the degrees with an O(N*E) Python loop and
+        selects with torch.topk, whose choice among EQUAL degrees at the cut is implementation-defined; here the degrees are a
+        device histogram and the exact radix select breaks ties towards the lower node index."""
+        if self.device is None:
+            raise KernelError("TissueGraphBuilder needs a CUDA (B200) device; there is no CPU fallback")
+        from . import ops
+        n = int(graph.num_nodes)
+        k = max(1, int(n * pool_ratio))
+        if k >= n:
+            return graph
+        dev = self.device
+        ei = graph.edge_index.to(dev)
+        if ei.numel() > 0:
+            deg = torch.bincount(ei.reshape(-1), minlength=n).to(torch.float32)      # out-degree + in-degree
+        else:
+            deg = torch.zeros(n, dtype=torch.float32, device=dev)
+        perm, node_map = ops.topk_select(deg.contiguous(), k)
+        keep = perm.long()
+        nm = node_map.long()
+        host = graph.x.device
+        if ei.numel() > 0:
+            emask = (nm[ei[0]] >= 0) & (nm[ei[1]] >= 0)
+            new_ei = nm[ei[:, emask]].to(host)
+            ea = graph.edge_attr
+            new_ea = ea[emask.to(ea.device)] if ea is not None and ea.numel() > 0 else torch.empty((0, 1))
+        else:
+            new_ei, new_ea = torch.empty((2, 0), dtype=torch.long), torch.empty((0, 1), dtype=torch.float)
+        kh = keep.to(host)
+        return Data(x=graph.x[kh], edge_index=new_ei, edge_attr=new_ea, pos=graph.pos[kh], num_nodes=k)
 
     def _create_empty_graph(self):
         return Data(x=torch.empty((0, self.feature_dim), dtype=torch.float), edge_index=torch.empty((2, 0), dtype=torch.long),

@@ -160,9 +160,7 @@ def linear(a, w, bias=None, *, r_pre=None, act_pre=None, ln1=None, ln2=None, act
         dot_out = torch.empty(M, dtype=torch.float32, device=a.device)
         p.dot_w, p.dot_b, p.dot_act, p.dot_out = _p(dot[0]), float(dot[1]), ACT[dot[2]], _p(dot_out)
     p.a_scale = float(a_scale)
-    keep = None
     if row_bias is not None:
-        keep = row_bias
         p.row_bias_index, p.row_bias, p.ld_row_bias = _p(row_bias[0]), _p(row_bias[1]), row_bias[1].stride(0)
     if peers:
         assert out is not None and mode != "simt" and N <= 512 and len(peers) <= 8

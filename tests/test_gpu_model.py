@@ -202,3 +202,29 @@ def test_builder_tensor_core_candidate_path_is_exact():
     finally:
         builder.TC_MIN_ROWS = old
     assert np.array_equal(gph.edge_index.numpy(), gld["edge_index"])
+
+
+def test_hierarchical_graph_pooling_vs_reference_semantics():
+    """create_hierarchical_graph / _pool_graph (preprocessing/tissue_graph_builder.py:449-516) restated in plain torch on the CPU
+    (degree = occurrences in edge_index, keep the top half, relabel). torch.topk's choice among equal degrees at the cut is
+    implementation-defined, so the kept sets must agree on every node strictly above the cut degree and may differ only among
+    nodes AT the cut degree; everything derived (features, edges) must be consistent with the kept set."""
+    from dgdm_histopath_lab_b200 import TissueGraphBuilder
+    d = synth.tile_graph(700, 16, seed=9)
+    gs = TissueGraphBuilder(feature_extractor="none").create_hierarchical_graph(d, levels=3)
+    assert [g.num_nodes for g in gs] == [700, 350, 175]
+    cur = d
+    for lvl in range(1, 3):
+        n, k = cur.num_nodes, max(1, int(cur.num_nodes * 0.5))
+        deg = torch.bincount(cur.edge_index.reshape(-1), minlength=n)
+        cut = torch.sort(deg, descending=True)[0][k - 1]
+        g = gs[lvl]
+        # recover which nodes were kept from their (unique, continuous-valued) features
+        kept = torch.tensor([int(torch.nonzero((cur.x == row).all(1))[0]) for row in g.x])
+        assert torch.equal(kept, torch.sort(kept)[0]) and kept.numel() == k
+        assert set(torch.nonzero(deg > cut).reshape(-1).tolist()) <= set(kept.tolist())
+        assert (deg[kept] >= cut).all()
+        nm = torch.full((n,), -1, dtype=torch.long); nm[kept] = torch.arange(k)
+        em = (nm[cur.edge_index[0]] >= 0) & (nm[cur.edge_index[1]] >= 0)
+        assert torch.equal(g.edge_index, nm[cur.edge_index[:, em]]) and torch.equal(g.pos, cur.pos[kept])
+        cur = g

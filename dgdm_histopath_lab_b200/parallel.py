@@ -93,7 +93,10 @@ class SymmComm(TorchDistComm):
             t = symm_mem.empty(self.max_floats, dtype=torch.float32, device=device)
             self.hdls.append(symm_mem.rendezvous(t, self._pg))
             self.bufs.append(t)
-        self.multicast = bool(use_multicast) and all(int(getattr(h, "multicast_ptr", 0) or 0) != 0 for h in self.hdls)
+        # measured on B200 (tools/halo_bench.py, [100k, 512] fp32): 4 GPUs — P2P stores 275 us vs NVLS multicast 326 us vs NCCL
+        # all_gather 320 us (+86 us GEMM); 8 GPUs — 319 vs 326 vs 316 (+45) us: all NVLink-inbound-bound (~560 GB/s per GPU).
+        # Multicast needs 1/(P-1) of the SM->NVLink egress, so it is used from 8 ranks up, plain P2P stores below.
+        self.multicast = bool(use_multicast) and self.world >= 8 and all(int(getattr(h, "multicast_ptr", 0) or 0) != 0 for h in self.hdls)
         self._k = 0
 
     def fused_linear_gather(self, linear_fn, part, n_cols):

@@ -132,19 +132,29 @@ def _knn_cosine_tc(features, k, q0, nq, chunk=None):
     return idx, cos, dist
 
 
-def knn2d(coords, k, q0=0, nq=None, chunk=None):
-    """coords: float64 CUDA [n,2]. Returns (idx int32 [nq,k], dist float64 [nq,k])."""
+GRID_MIN_ROWS = 2048        # below this the brute-force 2-D kNN is used
+
+
+def knn2d(coords, k, q0=0, nq=None, chunk=None, mode=None):
+    """coords: float64 CUDA [n,2]. Returns (idx int32 [nq,k], dist float64 [nq,k]). mode 'grid' (default for n >= GRID_MIN_ROWS):
+    uniform-grid ring search, O(N); mode 'brute': fp64 distance rows, O(N^2). Identical results."""
     lib = _lib.load()
     n = coords.size(0)
     nq = n - q0 if nq is None else nq
     dev = coords.device
     idx = torch.empty(nq, k, dtype=torch.int32, device=dev)
     dist = torch.empty(nq, k, dtype=torch.float64, device=dev)
+    if mode is None:
+        mode = "grid" if n >= GRID_MIN_ROWS else "brute"
+    if mode == "grid":
+        work = torch.empty(int(lib.dgdm_knn2d_grid_work_bytes(n)), dtype=torch.uint8, device=dev)
+        _check(lib.dgdm_knn2d(_p(coords), n, q0, nq, k, _p(idx), _p(dist), 1, _p(work), _stream()), "dgdm_knn2d")
+        return idx, dist
     if chunk is None:
         chunk = max(64, min(nq, int(2e9 // (8 * n))))
     for c0 in range(0, nq, chunk):
         cn = min(chunk, nq - c0)
-        _check(lib.dgdm_knn2d(_p(coords), n, q0 + c0, cn, k, _p(idx[c0:]), _p(dist[c0:]), _stream()), "dgdm_knn2d")
+        _check(lib.dgdm_knn2d(_p(coords), n, q0 + c0, cn, k, _p(idx[c0:]), _p(dist[c0:]), 0, None, _stream()), "dgdm_knn2d")
     return idx, dist
 
 
@@ -170,6 +180,52 @@ def candidate_edges(sp_idx, sp_dist, mo_idx, mo_cos, threshold, row0=0):
         return dict(src=z.astype(np.int64), tgt=z.astype(np.int64), type=z.astype(np.int64), weight=z, f0=z, f1=z)
     cat = [np.concatenate([o[i] for o in out]) for i in range(6)]
     return dict(src=cat[0].astype(np.int64), tgt=cat[1], type=cat[2], weight=cat[3], f0=cat[4], f1=cat[5])
+
+
+def candidate_edges_device(sp_idx, sp_dist, mo_idx, mo_cos, threshold, row0=0):
+    """candidate_edges on device tensors (same emission order: spatial rows then morphological rows, row-major)."""
+    dev = sp_idx.device if sp_idx is not None else mo_idx.device
+    parts = []
+    if sp_idx is not None and sp_idx.size(1) > 1:
+        d = sp_dist[:, 1:]
+        w = torch.exp(-d * 10)
+        keep = w >= threshold
+        src = (torch.arange(sp_idx.size(0), device=dev)[:, None] + row0).expand_as(d)
+        parts.append((src[keep], sp_idx[:, 1:][keep].long(), torch.zeros(int(keep.sum()), dtype=torch.long, device=dev), w[keep], d[keep], w[keep]))
+    if mo_idx is not None and mo_idx.size(1) > 1:
+        sm = mo_cos[:, 1:]
+        keep = sm >= torch.tensor(threshold, dtype=torch.float32, device=dev)       # float32 compare, like the reference's fp32 matrix
+        src = (torch.arange(mo_idx.size(0), device=dev)[:, None] + row0).expand_as(sm)
+        sv = sm[keep].double()
+        parts.append((src[keep], mo_idx[:, 1:][keep].long(), torch.ones(int(keep.sum()), dtype=torch.long, device=dev), sv, sv, torch.zeros_like(sv)))
+    names = ("src", "tgt", "type", "weight", "f0", "f1")
+    if not parts:
+        z = torch.zeros(0, device=dev)
+        return {k: (z.long() if k in ("src", "tgt", "type") else z.double()) for k in names}
+    return {k: torch.cat([p[i] for p in parts]) for i, k in enumerate(names)}
+
+
+def remove_duplicate_edges_device(e, n):
+    """remove_duplicate_edges on the device: two stable sorts give (key, -weight, first-seen) order; the winner of a key is the
+    first row of its group, and groups are emitted in the order of their first occurrence."""
+    m = e["src"].numel()
+    if m == 0:
+        return e
+    a, b = torch.minimum(e["src"], e["tgt"]), torch.maximum(e["src"], e["tgt"])
+    key = a * n + b
+    by_w = torch.sort(-e["weight"], stable=True).indices
+    by_k = torch.sort(key[by_w], stable=True).indices
+    srt = by_w[by_k]
+    ks = key[srt]
+    first = torch.ones(m, dtype=torch.bool, device=key.device)
+    first[1:] = ks[1:] != ks[:-1]
+    winners = srt[first]
+    pos_sorted = torch.sort(key, stable=True)
+    kfirst = torch.ones(m, dtype=torch.bool, device=key.device)
+    kfirst[1:] = pos_sorted.values[1:] != pos_sorted.values[:-1]
+    first_pos = pos_sorted.indices[kfirst]                          # first occurrence of each key, keys ascending (like `winners`)
+    emit = winners[torch.sort(first_pos, stable=True).indices]
+    return {k: v[emit] for k, v in e.items()}
 
 
 def remove_duplicate_edges(e, n):
@@ -242,9 +298,10 @@ class TissueGraphBuilder:
         ks, km = min(self.spatial_k + 1, n), min(self.morphological_k + 1, n)
         sp_idx, sp_dist = knn2d(c, ks)
         mo_idx, mo_cos, _ = knn_cosine(f, km)
-        e = candidate_edges(sp_idx.cpu().numpy(), sp_dist.cpu().numpy(), mo_idx.cpu().numpy(), mo_cos.cpu().numpy(),
-                            self.edge_threshold)
-        return remove_duplicate_edges(e, n)
+        # thresholds, undirected de-duplication and ordering stay on the device (index bookkeeping through torch's sort);
+        # only the surviving edges come back to the host
+        e = remove_duplicate_edges_device(candidate_edges_device(sp_idx, sp_dist, mo_idx, mo_cos, self.edge_threshold), n)
+        return {k: v.cpu().numpy() for k, v in e.items()}
 
     def build_graph(self, slide_data, patch_images=None):
         nodes = self._create_nodes(slide_data, patch_images)

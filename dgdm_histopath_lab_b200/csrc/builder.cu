@@ -78,6 +78,141 @@ __global__ void __launch_bounds__(256) dist2d_kernel(const double* __restrict__ 
 
 __device__ __forceinline__ bool knn_less(double da, int ia, double db, int ib) { return da < db || (da == db && ia < ib); }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Exact 2-D k nearest neighbours on a uniform grid (spatial edges, preprocessing/tissue_graph_builder.py:290-320): O(N) instead
+// of the O(N^2) distance matrix. Points are binned into G x G cells over their bounding box (counting sort by cell); a query
+// scans the cells ring by ring (Chebyshev distance r around its own cell) and stops after ring r once it holds k candidates whose
+// k-th squared distance is strictly below (r*h + m)^2, h = cell size, m = distance from the query to the nearest edge of its
+// cell — every unvisited cell lies at least that far away. Distances are fp64 direct differences and ties break towards the lower
+// index, exactly like the brute-force kernel, so the result is identical to it (and to sklearn's kd-tree on tie-free data).
+struct Grid2D { double x0, y0, inv_h, h; int G; };
+
+__global__ void grid_bbox_kernel(const double* __restrict__ P, int n, double* __restrict__ bb /*minx,miny,maxx,maxy*/) {
+  __shared__ double sm[4][32];
+  double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double x = P[2 * (size_t)i], y = P[2 * (size_t)i + 1];
+    mnx = fmin(mnx, x); mny = fmin(mny, y); mxx = fmax(mxx, x); mxy = fmax(mxy, y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mnx = fmin(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mny = fmin(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+    mxx = fmax(mxx, __shfl_xor_sync(0xffffffffu, mxx, o)); mxy = fmax(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+  }
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { sm[0][w] = mnx; sm[1][w] = mny; sm[2][w] = mxx; sm[3][w] = mxy; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) { mnx = fmin(mnx, sm[0][i]); mny = fmin(mny, sm[1][i]); mxx = fmax(mxx, sm[2][i]); mxy = fmax(mxy, sm[3][i]); }
+    bb[0] = mnx; bb[1] = mny; bb[2] = mxx; bb[3] = mxy;
+  }
+}
+__device__ __forceinline__ Grid2D grid_from_bbox(const double* bb, int G) {
+  Grid2D g;
+  const double ext = fmax(fmax(bb[2] - bb[0], bb[3] - bb[1]), 1e-300);
+  g.x0 = bb[0]; g.y0 = bb[1]; g.G = G; g.h = ext / (double)G; g.inv_h = (double)G / ext;
+  return g;
+}
+__device__ __forceinline__ int grid_cell(const Grid2D& g, double v, double v0) {
+  int c = (int)floor((v - v0) * g.inv_h);
+  return c < 0 ? 0 : (c >= g.G ? g.G - 1 : c);
+}
+__global__ void grid_count_kernel(const double* __restrict__ P, int n, const double* __restrict__ bb, int G, int* __restrict__ cell_of,
+                                  int* __restrict__ counts) {
+  const Grid2D g = grid_from_bbox(bb, G);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int c = grid_cell(g, P[2 * (size_t)i + 1], g.y0) * G + grid_cell(g, P[2 * (size_t)i], g.x0);
+    cell_of[i] = c;
+    atomicAdd(counts + c, 1);
+  }
+}
+// exclusive scan of counts[0..m) into start[0..m] by one block
+__global__ void __launch_bounds__(1024) grid_scan_kernel(const int* __restrict__ counts, int* __restrict__ start, int m) {
+  __shared__ int wt[32];
+  __shared__ int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < m; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < m ? counts[i] : 0;
+    int sc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc += t; }
+    if (lane == 31) wt[warp] = sc;
+    __syncthreads();
+    if (warp == 0) {
+      int w = wt[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+      wt[lane] = w;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    if (i < m) start[i] = carry + (warp ? wt[warp - 1] : 0) + sc - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + wt[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) start[m] = carry_s;
+}
+__global__ void grid_fill_kernel(const int* __restrict__ cell_of, int n, const int* __restrict__ start, int* __restrict__ cursor,
+                                 int* __restrict__ sorted_idx) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int c = cell_of[i];
+    sorted_idx[start[c] + atomicAdd(cursor + c, 1)] = i;      // order inside a cell is irrelevant: selection is by (distance, index)
+  }
+}
+template <int K>
+__global__ void __launch_bounds__(128) grid_knn_kernel(const double* __restrict__ P, int n, int q0, int nq, int k, const double* __restrict__ bb,
+                                                       int G, const int* __restrict__ start, const int* __restrict__ sorted_idx,
+                                                       int* __restrict__ idx_out, double* __restrict__ dist_out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const Grid2D g = grid_from_bbox(bb, G);
+  const double qx = P[2 * (size_t)(q0 + q)], qy = P[2 * (size_t)(q0 + q) + 1];
+  const int cx = grid_cell(g, qx, g.x0), cy = grid_cell(g, qy, g.y0);
+  double bd[K]; int bi[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) { bd[i] = INFINITY; bi[i] = 0x7fffffff; }
+  // distance from the query to the nearest edge of its own cell (0 if the point was clamped into the cell)
+  const double lx = qx - (g.x0 + cx * g.h), ly = qy - (g.y0 + cy * g.h);
+  double m = fmin(fmin(lx, g.h - lx), fmin(ly, g.h - ly));
+  if (!(m > 0.0)) m = 0.0;
+  auto visit = [&](int ccx, int ccy) {
+    const int c = ccy * G + ccx;
+    for (int s = start[c]; s < start[c + 1]; ++s) {
+      const int j = sorted_idx[s];
+      const double dx = qx - P[2 * (size_t)j], dy = qy - P[2 * (size_t)j + 1];
+      const double d2 = dx * dx + dy * dy;
+      if (knn_less(d2, j, bd[k - 1], bi[k - 1])) {
+        int p = k - 1;
+        while (p > 0 && knn_less(d2, j, bd[p - 1], bi[p - 1])) { bd[p] = bd[p - 1]; bi[p] = bi[p - 1]; --p; }
+        bd[p] = d2; bi[p] = j;
+      }
+    }
+  };
+  for (int r = 0; r < G; ++r) {
+    const int x_lo = cx - r, x_hi = cx + r, y_lo = cy - r, y_hi = cy + r;
+    if (r == 0) visit(cx, cy);
+    else {
+      for (int xx = max(x_lo, 0); xx <= min(x_hi, G - 1); ++xx) {
+        if (y_lo >= 0) visit(xx, y_lo);
+        if (y_hi < G) visit(xx, y_hi);
+      }
+      for (int yy = max(y_lo + 1, 0); yy <= min(y_hi - 1, G - 1); ++yy) {
+        if (x_lo >= 0) visit(x_lo, yy);
+        if (x_hi < G) visit(x_hi, yy);
+      }
+    }
+    if (x_lo <= 0 && y_lo <= 0 && x_hi >= G - 1 && y_hi >= G - 1) break;        // whole grid visited
+    const double bound = ((double)r * g.h + m) * (1.0 - 1e-12);
+    if (bi[k - 1] != 0x7fffffff && bd[k - 1] < bound * bound) break;
+  }
+  for (int o = 0; o < k; ++o) { idx_out[(size_t)q * k + o] = bi[o]; dist_out[(size_t)q * k + o] = sqrt(bd[o]); }
+}
+
+
 // warp per row: the K smallest (value, index) pairs of D2[row, 0..n), ascending. Each lane keeps a sorted private list
 // over its strided elements (in shared memory), then a 32-way merge picks the global K.
 template <int K>
@@ -346,9 +481,44 @@ extern "C" int dgdm_knn_cosine_tc(const float* F, const void* W_img, const doubl
   return DGDM_OK;
 }
 
-extern "C" int dgdm_knn2d(const double* coords, int n, int q0, int nq, int k, int* nbr_idx, double* nbr_dist, void* stream) {
+extern "C" size_t dgdm_knn2d_grid_work_bytes(int n) {
+  int G = (int)ceil(sqrt((double)n / 3.0)); if (G < 1) G = 1;
+  return al256(4 * 8) + al256((size_t)n * 4) * 2 + al256(((size_t)G * G + 1) * 4) * 3 + 256;
+}
+static int knn2d_grid(const double* coords, int n, int q0, int nq, int k, int* nbr_idx, double* nbr_dist, void* work, cudaStream_t s) {
+  int G = (int)ceil(sqrt((double)n / 3.0)); if (G < 1) G = 1;
+  const size_t cells = (size_t)G * G;
+  uint8_t* w = (uint8_t*)(((uintptr_t)work + 255) & ~(uintptr_t)255);
+  double* bb = (double*)w; w += al256(4 * 8);
+  int* cell_of = (int*)w; w += al256((size_t)n * 4);
+  int* sorted_idx = (int*)w; w += al256((size_t)n * 4);
+  int* counts = (int*)w; w += al256((cells + 1) * 4);
+  int* start = (int*)w; w += al256((cells + 1) * 4);
+  int* cursor = (int*)w;
+  if (cudaMemsetAsync(counts, 0, (cells + 1) * 4, s) != cudaSuccess || cudaMemsetAsync(cursor, 0, (cells + 1) * 4, s) != cudaSuccess) return DGDM_ERR_LAUNCH;
+  grid_bbox_kernel<<<1, 1024, 0, s>>>(coords, n, bb);
+  const int blocks = (n + 255) / 256 > 148 * 8 ? 148 * 8 : (n + 255) / 256;
+  grid_count_kernel<<<blocks, 256, 0, s>>>(coords, n, bb, G, cell_of, counts);
+  grid_scan_kernel<<<1, 1024, 0, s>>>(counts, start, (int)cells);
+  grid_fill_kernel<<<blocks, 256, 0, s>>>(cell_of, n, start, cursor, sorted_idx);
+  const int qb = (nq + 127) / 128;
+  if (k <= 16) grid_knn_kernel<16><<<qb, 128, 0, s>>>(coords, n, q0, nq, k, bb, G, start, sorted_idx, nbr_idx, nbr_dist);
+  else if (k <= 32) grid_knn_kernel<32><<<qb, 128, 0, s>>>(coords, n, q0, nq, k, bb, G, start, sorted_idx, nbr_idx, nbr_dist);
+  else grid_knn_kernel<KNN_MAXK><<<qb, 128, 0, s>>>(coords, n, q0, nq, k, bb, G, start, sorted_idx, nbr_idx, nbr_dist);
+  if (cudaGetLastError() != cudaSuccess) return DGDM_ERR_LAUNCH;
+  return DGDM_OK;
+}
+
+// mode 0: brute force (O(N^2) fp64 distance rows, small n); mode 1: uniform grid (O(N)); work: dgdm_knn2d_grid_work_bytes(n)
+// bytes for mode 1 (may be NULL for mode 0). Both return identical results.
+extern "C" int dgdm_knn2d(const double* coords, int n, int q0, int nq, int k, int* nbr_idx, double* nbr_dist, int mode, void* work,
+                          void* stream) {
   if (!coords || !nbr_idx || !nbr_dist || n <= 0 || k <= 0 || k > KNN_MAXK || k > n || q0 < 0 || nq <= 0 || q0 + nq > n) return DGDM_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
+  if (mode == 1) {
+    if (!work) return DGDM_ERR_INVALID;
+    return knn2d_grid(coords, n, q0, nq, k, nbr_idx, nbr_dist, work, s);
+  }
   double* D2 = nullptr;
   // scratch for the distance rows of this query chunk (stream-ordered allocation; freed below)
   if (cudaMallocAsync((void**)&D2, (size_t)nq * n * sizeof(double), s) != cudaSuccess) return DGDM_ERR_LAUNCH;

@@ -209,8 +209,10 @@ int dgdm_knn_cosine_tc(const float* F, const void* W_img, const double* sq, int 
  * K-block 0, w_plane_stride_bytes = (rows of the whole image) * 128; p->N <= 512; plain product (no epilogue fields needed). */
 int dgdm_gemm_f16x2_strided(const dgdm_gemm_params* p, long long w_plane_stride_bytes, void* stream);
 /* _create_spatial_edges (:290-320): exact k nearest neighbours on 2-D fp64 coords (query row included, callers pass
- * spatial_k+1), ascending distance, ties towards the lower index. */
-int dgdm_knn2d(const double* coords, int n, int q0, int nq, int k, int* nbr_idx, double* nbr_dist, void* stream);
+ * spatial_k+1), ascending distance, ties towards the lower index. mode 0: brute force over fp64 distance rows (small n);
+ * mode 1: uniform-grid ring search, O(N), identical results; work = dgdm_knn2d_grid_work_bytes(n) bytes (mode 1 only). */
+size_t dgdm_knn2d_grid_work_bytes(int n);
+int dgdm_knn2d(const double* coords, int n, int q0, int nq, int k, int* nbr_idx, double* nbr_dist, int mode, void* work, void* stream);
 
 #ifdef __cplusplus
 }

@@ -195,12 +195,12 @@ def test_builder_tensor_core_candidate_path_is_exact():
     feats = synth.clustered_features(600, d=64, num_clusters=12, seed=21, sigma_lo=0.05, sigma_hi=0.11)
     xs, ys, dims = synth.jittered_grid_coords(600, seed=21, extent=3000)
     patches = [PatchInfo(int(xs[i]), int(ys[i]), 0, 20.0, f"s_patch_{i:06d}", 0.9, feats[i]) for i in range(600)]
-    old = builder.TC_MIN_ROWS
-    builder.TC_MIN_ROWS = 1
+    old = builder.TC_MIN_ROWS, builder.GRID_MIN_ROWS
+    builder.TC_MIN_ROWS = builder.GRID_MIN_ROWS = 1          # force the tensor-core Gram path and the grid 2-D kNN
     try:
         gph = TissueGraphBuilder(feature_extractor="none").build_graph(SlideData("s", patches, {"dimensions": dims}))
     finally:
-        builder.TC_MIN_ROWS = old
+        builder.TC_MIN_ROWS, builder.GRID_MIN_ROWS = old
     assert np.array_equal(gph.edge_index.numpy(), gld["edge_index"])
 
 
@@ -228,3 +228,67 @@ def test_hierarchical_graph_pooling_vs_reference_semantics():
         em = (nm[cur.edge_index[0]] >= 0) & (nm[cur.edge_index[1]] >= 0)
         assert torch.equal(g.edge_index, nm[cur.edge_index[:, em]]) and torch.equal(g.pos, cur.pos[kept])
         cur = g
+
+
+def test_device_prefetcher_streams_graphs_in_order_and_reuses_buffers():
+    """loader.DevicePrefetcher: graphs arrive on the device unchanged and in order, staging buffers are reused (two slots),
+    row-restricted staging (node-partitioned ranks) carries num_nodes, and the model output equals the plain .to(device) path."""
+    from dgdm_histopath_lab_b200.loader import DevicePrefetcher
+    m = make_model(SMALL_CFG).to(DEV)
+    graphs = [synth.tile_graph(200 + 10 * (i % 2), 48, seed=50 + i).pin_memory() for i in range(5)]
+    ptrs = set()
+    for i, d in enumerate(DevicePrefetcher(graphs, DEV)):
+        assert torch.equal(d.x.cpu(), graphs[i].x) and torch.equal(d.edge_index.cpu(), graphs[i].edge_index)
+        ptrs.add(d.x.data_ptr())
+        out = m(d)["graph_embedding"]
+        ref = m(graphs[i].to(DEV))["graph_embedding"]
+        assert torch.equal(out, ref)
+    assert len(ptrs) <= 4                      # two slots (re-allocated once when the node count changes)
+    part = list(DevicePrefetcher(graphs[:1], DEV, rows=(50, 120)))[0]
+    assert part.x.shape == (70, 48) and part.num_nodes == 200 and torch.equal(part.x.cpu(), graphs[0].x[50:120])
+
+
+@pytest.mark.parametrize("kind", ["uniform", "jittered_grid", "clustered_with_duplicates", "collinear"])
+def test_knn2d_grid_equals_brute_force(kind):
+    """uniform-grid ring search (O(N)) vs the brute-force fp64 distance rows: identical indices, order and distances, including
+    exact ties (duplicate points / regular spacing resolve towards the lower index in both) and degenerate bounding boxes."""
+    from dgdm_histopath_lab_b200 import builder
+    g = torch.Generator().manual_seed(11)
+    n, k = 6000, 9
+    if kind == "uniform":
+        c = torch.rand(n, 2, generator=g, dtype=torch.float64)
+    elif kind == "jittered_grid":
+        xs, ys, dims = synth.jittered_grid_coords(n, seed=4, extent=50000)
+        c = torch.tensor(np.stack([xs / dims[0], ys / dims[1]], 1), dtype=torch.float64)
+    elif kind == "clustered_with_duplicates":
+        centres = torch.rand(30, 2, generator=g, dtype=torch.float64)
+        c = centres[torch.randint(0, 30, (n,), generator=g)] + 0.003 * torch.randn(n, 2, generator=g, dtype=torch.float64)
+        c[1000:1200] = c[0]                                        # 201 coincident points: all ties
+    else:
+        c = torch.stack([torch.linspace(0, 1, n, dtype=torch.float64), torch.zeros(n, dtype=torch.float64)], 1)   # regular spacing, zero height
+    c = c.to(DEV).contiguous()
+    ib, db = builder.knn2d(c, k, mode="brute")
+    ig, dg = builder.knn2d(c, k, mode="grid")
+    assert torch.equal(ig, ib) and torch.equal(dg, db)
+    i2, d2 = builder.knn2d(c, k, q0=777, nq=500, mode="grid")      # a shard of the query rows
+    assert torch.equal(i2, ib[777:1277]) and torch.equal(d2, db[777:1277])
+
+
+def test_builder_device_dedup_equals_host_restatement():
+    """candidate thresholds + undirected de-duplication on the device (stable sorts) vs the numpy restatement of the reference's
+    dict loop (strictly-greater weight replaces, first-seen position kept), on a graph where many pairs occur 2-4 times."""
+    from dgdm_histopath_lab_b200 import builder
+    n = 5000
+    f = torch.as_tensor(synth.clustered_features(n, d=64, num_clusters=25, seed=2, sigma_lo=0.05, sigma_hi=0.11)).float().to(DEV)
+    xs, ys, dims = synth.jittered_grid_coords(n, seed=2, extent=20000)
+    c = torch.tensor(np.stack([xs / dims[0], ys / dims[1]], 1), dtype=torch.float64, device=DEV)
+    sp_idx, sp_dist = builder.knn2d(c, 9)
+    mo_idx, mo_cos, _ = builder.knn_cosine(f, 17)
+    host = builder.remove_duplicate_edges(builder.candidate_edges(sp_idx.cpu().numpy(), sp_dist.cpu().numpy(), mo_idx.cpu().numpy(),
+                                                                    mo_cos.cpu().numpy(), 0.7), n)
+    dev = builder.remove_duplicate_edges_device(builder.candidate_edges_device(sp_idx, sp_dist, mo_idx, mo_cos, 0.7), n)
+    assert host["src"].shape[0] > 10000
+    for k in ("src", "tgt", "type"):
+        assert np.array_equal(dev[k].cpu().numpy(), host[k]), k
+    for k in ("weight", "f0", "f1"):
+        assert np.abs(dev[k].cpu().numpy() - host[k]).max() < 1e-15, k          # exp() on the device vs numpy: last-bit differences only

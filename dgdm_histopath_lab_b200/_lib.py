@@ -54,9 +54,9 @@ SIGNATURES = {
                                             c_void_p, c_void_p]),
     "dgdm_segment_minmax": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "dgdm_spatial_pe_add": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
-    "dgdm_spatial_attention_work_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "dgdm_spatial_attention_work_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "dgdm_spatial_attention": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
-                                       c_int, c_int, c_int, c_float, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+                                       c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "dgdm_spatial_attention_weights": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "dgdm_attention_pool_work_floats": (c_size_t, [c_int, c_int, c_int, c_int]),
     "dgdm_attention_pool": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

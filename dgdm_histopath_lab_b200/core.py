@@ -431,10 +431,11 @@ class SpatialAttention(nn.Module):
             raise NotImplementedError(f"SpatialAttention head_dim {self.head_dim}: supported head widths are 4, 8, 16, 32, 64")
         pos = pos.float().contiguous()
         w, bias = att.qkv_weight()
+        max_seg = max((seg_host[i + 1] - seg_host[i] for i in range(num_seg)), default=0) if seg_host is not None else 0
         if part is None:
             xp = ops.spatial_pe_add(x, pos, seg_ptr, num_seg)
             qkv = ops.linear(xp, w, bias)
-            o = ops.spatial_attention(qkv, pos, seg_ptr, num_seg, self.num_heads, self.temperature)
+            o = ops.spatial_attention(qkv, pos, seg_ptr, num_seg, self.num_heads, self.temperature, max_seg=max_seg)
         else:
             if need_weights:
                 raise NotImplementedError("return_attention is not available for node-partitioned graphs")
@@ -444,7 +445,7 @@ class SpatialAttention(nn.Module):
             qkv = ops.linear(xp, w, bias)
             qkv_full = part.gather(qkv)
             o = ops.spatial_attention(qkv, pos_l, qseg, num_seg, self.num_heads, self.temperature,
-                                      kv_qkv=qkv_full, kv_pos=pos, kseg_ptr=seg_ptr)
+                                      kv_qkv=qkv_full, kv_pos=pos, kseg_ptr=seg_ptr, max_seg=max_seg)
         out = ops.linear(o, split_weight(att.out_proj.weight), att.out_proj.bias.detach(), r_pre=x, ln1=_ln(self.norm))
         weights = None
         if need_weights:

@@ -575,18 +575,18 @@ int attn_simt_launch(const float* q_qkv, int ld_q, const float* q_pos, const int
                      const float* kv_qkv, int ld_kv, const float* kv_pos, const int* kseg_ptr, int num_seg,
                      int D, int heads, float temperature, float* out, int ldo, cudaStream_t s);
 // attention_tc.cu: tcgen05 / TMEM path (D = 128, 8 heads)
-size_t attn_tc_work_bytes(int Nq, int Nkv, int D, int heads, int num_seg);
+size_t attn_tc_work_bytes(int Nq, int Nkv, int D, int heads, int num_seg, int max_seg_keys);
 int attn_tc_launch(const float* q_qkv, int ld_q, const float* q_pos, const int* qseg_ptr, int Nq,
                    const float* kv_qkv, int ld_kv, const float* kv_pos, const int* kseg_ptr, int Nkv,
-                   int num_seg, float temperature, float* out, int ldo, void* work, size_t work_bytes, cudaStream_t s);
+                   int num_seg, int max_seg_keys, float temperature, float* out, int ldo, void* work, size_t work_bytes, cudaStream_t s);
 
 }  // namespace dgdm
 using namespace dgdm;
 
-extern "C" size_t dgdm_spatial_attention_work_bytes(int Nq, int Nkv, int D, int heads, int num_seg) {
+extern "C" size_t dgdm_spatial_attention_work_bytes(int Nq, int Nkv, int D, int heads, int num_seg, int max_seg_keys) {
   const int ns = choose_nsplit(Nq, Nkv, num_seg);
   size_t b = 0;
-  if (D == 128 && heads == 8) b = attn_tc_work_bytes(Nq, Nkv, D, heads, num_seg);
+  if (D == 128 && heads == 8) b = attn_tc_work_bytes(Nq, Nkv, D, heads, num_seg, max_seg_keys);
   const size_t b_tc = b;
   b = 0;
   b += 2 * align256((size_t)Nq * D * 2);            // Qh, Ql
@@ -600,7 +600,7 @@ extern "C" size_t dgdm_spatial_attention_work_bytes(int Nq, int Nkv, int D, int 
 
 extern "C" int dgdm_spatial_attention(const float* q_qkv, int ld_q, const float* q_pos, const int* qseg_ptr, int Nq,
                                       const float* kv_qkv, int ld_kv, const float* kv_pos, const int* kseg_ptr, int Nkv,
-                                      int num_seg, int D, int heads, float temperature, int precise,
+                                      int num_seg, int max_seg_keys, int D, int heads, float temperature, int precise,
                                       float* out, int ldo, void* work, size_t work_bytes, void* stream) {
   if (!q_qkv || !kv_qkv || !qseg_ptr || !kseg_ptr || !out || !work) return DGDM_ERR_INVALID;
   if (heads <= 0 || D % heads != 0 || (ldo % 4) != 0) return DGDM_ERR_INVALID;
@@ -610,10 +610,10 @@ extern "C" int dgdm_spatial_attention(const float* q_qkv, int ld_q, const float*
   if (D / heads != 16 || precise == 3)      // other head widths (DGDM-Large 16 x 8) / forced: exact fp32 CUDA-core kernel
     return attn_simt_launch(q_qkv, ld_q, q_pos, qseg_ptr, Nq, kv_qkv, ld_kv, kv_pos, kseg_ptr, num_seg, D, heads, temperature, out, ldo,
                             (cudaStream_t)stream);
-  if (work_bytes < dgdm_spatial_attention_work_bytes(Nq, Nkv, D, heads, num_seg)) return DGDM_ERR_INVALID;
+  if (work_bytes < dgdm_spatial_attention_work_bytes(Nq, Nkv, D, heads, num_seg, max_seg_keys)) return DGDM_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
   if (precise == 1 && D == 128 && heads == 8)       // product path for DGDM-Base: tcgen05 / TMEM kernel (attention_tc.cu)
-    return attn_tc_launch(q_qkv, ld_q, q_pos, qseg_ptr, Nq, kv_qkv, ld_kv, kv_pos, kseg_ptr, Nkv, num_seg, temperature, out, ldo,
+    return attn_tc_launch(q_qkv, ld_q, q_pos, qseg_ptr, Nq, kv_qkv, ld_kv, kv_pos, kseg_ptr, Nkv, num_seg, max_seg_keys, temperature, out, ldo,
                           work, work_bytes, s);
   const int ns = choose_nsplit(Nq, Nkv, num_seg);
   uint8_t* w = (uint8_t*)(((uintptr_t)work + 255) & ~(uintptr_t)255);

@@ -473,22 +473,23 @@ static inline size_t tc_al256(size_t x) { return (x + 255) & ~(size_t)255; }
 // at TC_MAX_CHAIN key blocks per CTA (bias <= ~2e-5; 32 costs +1.1 ms at 100k nodes, 48 costs +0.5 ms); the partial (O, m, l) of the splits are merged in fp32 round-to-nearest
 // by attn_combine_kernel.
 constexpr int TC_MAX_CHAIN = 48;
-int attn_tc_nsplit(int Nq, int Nkv, int num_seg) {
+int attn_tc_nsplit(int Nq, int Nkv, int num_seg, int max_seg_keys) {
   const int tiles = (Nq + TC_QT - 1) / TC_QT + num_seg;
   int s = (148 * 8 + tiles - 1) / tiles;                       // aim for >= ~8 CTAs of work per SM
   const int avg_blocks = (Nkv / (num_seg > 0 ? num_seg : 1)) / TC_BN;
   const int max_s = avg_blocks / 8 > 1 ? avg_blocks / 8 : 1;   // at least ~8 key blocks per CTA
   if (s > max_s) s = max_s;
   if (s > 16) s = 16;
-  const int max_blocks = (Nkv + TC_BN - 1) / TC_BN;            // upper bound of any segment's block count
+  const int longest = (max_seg_keys > 0 && max_seg_keys < Nkv) ? max_seg_keys : Nkv;   // keys of the largest segment (Nkv when unknown)
+  const int max_blocks = (longest + TC_BN - 1) / TC_BN;
   const int s_chain = (max_blocks + TC_MAX_CHAIN - 1) / TC_MAX_CHAIN;
   if (s < s_chain) s = s_chain;
   if (s < 1) s = 1;
   return s;
 }
 
-size_t attn_tc_work_bytes(int Nq, int Nkv, int D, int heads, int num_seg) {
-  const int ns = attn_tc_nsplit(Nq, Nkv, num_seg);
+size_t attn_tc_work_bytes(int Nq, int Nkv, int D, int heads, int num_seg, int max_seg_keys) {
+  const int ns = attn_tc_nsplit(Nq, Nkv, num_seg, max_seg_keys);
   const size_t nblk_max = (size_t)(Nkv + TC_BN - 1) / TC_BN + (size_t)num_seg;
   size_t b = 1024;
   b += tc_al256(nblk_max * TC_IMG) + 1024;
@@ -504,10 +505,10 @@ void attn_launch_combine(const float* Opart, const float* Mpart, const float* Lp
 
 int attn_tc_launch(const float* q_qkv, int ld_q, const float* q_pos, const int* qseg_ptr, int Nq,
                    const float* kv_qkv, int ld_kv, const float* kv_pos, const int* kseg_ptr, int Nkv,
-                   int num_seg, float temperature, float* out, int ldo, void* work, size_t work_bytes, cudaStream_t s) {
+                   int num_seg, int max_seg_keys, float temperature, float* out, int ldo, void* work, size_t work_bytes, cudaStream_t s) {
   constexpr int D = 128, heads = 8;
-  if (work_bytes < attn_tc_work_bytes(Nq, Nkv, D, heads, num_seg)) return DGDM_ERR_INVALID;
-  const int ns = attn_tc_nsplit(Nq, Nkv, num_seg);
+  if (work_bytes < attn_tc_work_bytes(Nq, Nkv, D, heads, num_seg, max_seg_keys)) return DGDM_ERR_INVALID;
+  const int ns = attn_tc_nsplit(Nq, Nkv, num_seg, max_seg_keys);
   const size_t nblk_max = (size_t)(Nkv + TC_BN - 1) / TC_BN + (size_t)num_seg;
   uint8_t* w = (uint8_t*)(((uintptr_t)work + 1023) & ~(uintptr_t)1023);
   uint8_t* img = w; w += tc_al256(nblk_max * TC_IMG);

@@ -311,8 +311,9 @@ def attention_precise_default():
 
 
 def spatial_attention(qkv, pos, seg_ptr, num_seg, heads, temperature=1.0, *, kv_qkv=None, kv_pos=None, kseg_ptr=None,
-                      precise=None):
-    """Flash-style attention core. qkv [N, 3D] (q|k|v). pos may be None (no spatial bias). Returns [N, D]."""
+                      precise=None, max_seg=0):
+    """Flash-style attention core. qkv [N, 3D] (q|k|v). pos may be None (no spatial bias). Returns [N, D].
+    max_seg: number of keys of the largest segment when known on the host (0 = unknown)."""
     lib = _lib.load()
     Nq, D3 = qkv.shape
     D = D3 // 3
@@ -321,11 +322,12 @@ def spatial_attention(qkv, pos, seg_ptr, num_seg, heads, temperature=1.0, *, kv_
     kseg_ptr = seg_ptr if kseg_ptr is None else kseg_ptr
     Nkv = kv_qkv.size(0)
     precise = attention_precise_default() if precise is None else int(precise)
-    wb = int(lib.dgdm_spatial_attention_work_bytes(Nq, Nkv, D, heads, num_seg))
+    max_seg = Nkv if num_seg == 1 else int(max_seg)
+    wb = int(lib.dgdm_spatial_attention_work_bytes(Nq, Nkv, D, heads, num_seg, max_seg))
     work = torch.empty(wb, dtype=torch.uint8, device=qkv.device)
     out = torch.empty(Nq, D, dtype=torch.float32, device=qkv.device)
     _check(lib.dgdm_spatial_attention(_p(_f32c(qkv)), qkv.stride(0), _p(pos), _p(seg_ptr), Nq, _p(_f32c(kv_qkv)),
-                                      kv_qkv.stride(0), _p(kv_pos), _p(kseg_ptr), Nkv, num_seg, D, heads,
+                                      kv_qkv.stride(0), _p(kv_pos), _p(kseg_ptr), Nkv, num_seg, max_seg, D, heads,
                                       float(temperature), precise, _p(out), out.stride(0), _p(work), wb, _stream()),
            "dgdm_spatial_attention")
     return out

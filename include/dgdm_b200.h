@@ -145,15 +145,16 @@ int dgdm_spatial_pe_add(const float* X, int ldx, const float* pos, const int* se
 /* qkv: [N, 3*D] fp32 (q|k|v, biases included). out: [N, D] fp32 (heads concatenated, before out_proj).
  * kv_pos/kv_qkv allow the keys/values to come from a different (all-gathered) node set for node-partitioned
  * graphs: queries rows [0,Nq) use key segment [kseg_ptr[g], kseg_ptr[g+1]) of the kv arrays, with g = the
- * query's segment in qseg_ptr.  work: dgdm_spatial_attention_work_bytes(...) bytes.
+ * query's segment in qseg_ptr.  work: dgdm_spatial_attention_work_bytes(...) bytes. max_seg_keys: key count of the largest
+ * segment (0 = unknown, Nkv is assumed); it sizes the key splits that cap the tensor-core accumulation chain.
  * precise: 1 = product path, 3-term split-fp16 products (~fp32 accuracy): the tcgen05/TMEM kernel when D == 128 and heads == 8
  *             (DGDM-Base), else the mma.sync kernel; 2 = force the 3-term mma.sync kernel (comparison baseline);
  *          0 = single-pass fp16 operands on mma.sync (~1e-3, comparison only); 3 = force the exact fp32 CUDA-core kernel.
  * head_dim 16 runs on the tensor cores; head_dim 4/8/32/64 (DGDM-Large: 16 heads x 8) run on the exact fp32 CUDA-core kernel. */
-size_t dgdm_spatial_attention_work_bytes(int Nq, int Nkv, int D, int heads, int num_seg);
+size_t dgdm_spatial_attention_work_bytes(int Nq, int Nkv, int D, int heads, int num_seg, int max_seg_keys);
 int dgdm_spatial_attention(const float* q_qkv, int ld_q, const float* q_pos, const int* qseg_ptr, int Nq,
                            const float* kv_qkv, int ld_kv, const float* kv_pos, const int* kseg_ptr, int Nkv,
-                           int num_seg, int D, int heads, float temperature, int precise,
+                           int num_seg, int max_seg_keys, int D, int heads, float temperature, int precise,
                            float* out, int ldo, void* work, size_t work_bytes, void* stream);
 /* Head-averaged attention weights [n,n] of ONE graph segment (return_attention=True; O(n^2) output). */
 int dgdm_spatial_attention_weights(const float* qkv, int ld, const float* pos, int n, int D, int heads,

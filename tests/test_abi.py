@@ -23,7 +23,7 @@ def test_size_queries_are_pure_host_functions():
     lib = _lib.load()
     assert lib.dgdm_csr_build_work_ints(100, 1000) >= 2 * 101 + 1000
     assert lib.dgdm_topk_pool_work_ints(1000) >= 1000
-    assert lib.dgdm_spatial_attention_work_bytes(2000, 2000, 128, 8, 1) > 2000 * 128 * 2 * 6
+    assert lib.dgdm_spatial_attention_work_bytes(2000, 2000, 128, 8, 1, 0) > 2000 * 128 * 2 * 6
     assert lib.dgdm_attention_pool_work_floats(1000, 128, 8, 2) >= 8000
 
 

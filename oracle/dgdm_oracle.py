@@ -347,7 +347,13 @@ def dgdm_forward(sd, cfg, x, edge_index, edge_attr=None, batch=None, pos=None, m
             losses.append(F.mse_loss(eps, rng["target"][i]))                    # D13: independent target noise
         out["diffusion_loss"] = torch.stack(losses).mean()
         out["noisy_embeddings"] = xn.unsqueeze(0)                               # last graph only (dgdm_model.py:442-445)
-    g = global_attention_pool(sd, "global_pool", h, batch, heads)
+    pooling = cfg.get("pooling", "attention")
+    if pooling == "attention":
+        g = global_attention_pool(sd, "global_pool", h, batch, heads)
+    else:
+        # GlobalMeanPool / GlobalMaxPool / GlobalSet2SetPool (a mean in disguise), models/dgdm_model.py:552-585,618-642
+        groups = [torch.ones(h.size(0), dtype=torch.bool)] if batch is None else [batch == i for i in range(int(batch.max()) + 1)]
+        g = torch.stack([h[m].max(dim=0)[0] if pooling == "max" else h[m].mean(dim=0) for m in groups])
     out["graph_embedding"] = g
     out["node_embeddings"] = h
     if mode in ("inference", "finetune") and "classification_head.classifier.0.weight" in sd:

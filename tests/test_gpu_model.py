@@ -292,3 +292,17 @@ def test_builder_device_dedup_equals_host_restatement():
         assert np.array_equal(dev[k].cpu().numpy(), host[k]), k
     for k in ("weight", "f0", "f1"):
         assert np.abs(dev[k].cpu().numpy() - host[k]).max() < 1e-15, k          # exp() on the device vs numpy: last-bit differences only
+
+
+@pytest.mark.parametrize("activation,pooling", [("relu", "mean"), ("elu", "max"), ("gelu", "set2set")])
+def test_non_default_activation_and_pooling_options_vs_oracle(activation, pooling):
+    """SURVEY 8b 'non-default options': encoder activations relu / elu (epilogue switch) and the mean / max / set2set graph pools
+    (models/encoders.py:57-64, models/dgdm_model.py:244-257,552-585,618-642) against the oracle on a 2-graph batch."""
+    cfg = dict(SMALL_CFG, activation=activation, pooling=pooling)
+    m = make_model(cfg)
+    b = synth.tile_batch(2, 130, 48, seed=21)
+    ocfg = dict(oracle_cfg(cfg), activation=activation, pooling=pooling)
+    ref = O.dgdm_forward(sd_cpu(m), ocfg, b.x, b.edge_index, None, b.batch, b.pos)
+    out = m.to(DEV)(b.to(DEV), return_embeddings=True)
+    assert rel_err(out["node_embeddings"], ref["node_embeddings"])[0] < 1e-4
+    assert rel_err(out["graph_embedding"], ref["graph_embedding"])[0] < 1e-4

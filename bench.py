@@ -259,7 +259,7 @@ def main():
     att_exp = 8.0 * nq * N
     spmm_bytes = sum((e + n) * c * 4 + n * c * 4 + (e + n) * 8 + (n + 1) * 4 for (n, e, c) in meta.get("spmm", []))
     gemm_flops = sum(2.0 * m * k * n_ for (m, k, n_) in meta.get("gemm", []))
-    roof = {"kernel": "spatial_attn_kernel<16,precise>", "bound": "tensor", "achieved": att_flops / (att_ms * 1e-3) / 1e12 if att_ms else None,
+    roof = {"kernel": "spatial_attn_tc_kernel (+ prep / combine kernels of the same dgdm_spatial_attention call)", "bound": "tensor", "achieved": att_flops / (att_ms * 1e-3) / 1e12 if att_ms else None,
             "peak": pk["tf_sustained"], "unit": "TFLOP/s", "traffic": None, "peak_source": pk["src"],
             "note": "dominant kernel; exp2(MUFU)-bound, not tensor- or HBM-bound: head_dim 16 gives K=16 / N=16 MMAs",
             "gexp_per_s": att_exp / (att_ms * 1e-3) / 1e9 if att_ms else None, "ms": att_ms}

@@ -84,7 +84,8 @@ __device__ __forceinline__ void multimem_st4(float* mc, float4 t) {
 // thread-row-owned regs v[32] (row = lane) -> coalesced global store of rows [row0, row0+32), cols [c0, c0+32).
 // Node-partitioned graphs: the same 128-byte row segments also go to the peers' copies of C (P2P stores over NVLink, or one
 // NVLS multicast store that the switch replicates to every rank) — the halo all-gather fused into the GEMM epilogue.
-__device__ __forceinline__ void warp_store_tile(float* st, const float* v, const dgdm_gemm_params& p, int row0, int c0, int lane) {
+__device__ __forceinline__ void warp_store_tile(float* st, const float* v, float* G, int ldg, int row0, int c0,
+                                                int M, int N, int lane) {
 #pragma unroll
   for (int j = 0; j < 8; ++j)
     *reinterpret_cast<float4*>(st + lane * TR_STRIDE + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -93,19 +94,36 @@ __device__ __forceinline__ void warp_store_tile(float* st, const float* v, const
   for (int it = 0; it < 8; ++it) {
     int r = it * 4 + (lane >> 3), c = (lane & 7) * 4;
     float4 t = *reinterpret_cast<const float4*>(st + r * TR_STRIDE + c);
+    if (row0 + r < M && c0 + c < N) *reinterpret_cast<float4*>(G + (size_t)(row0 + r) * ldg + c0 + c) = t;
+  }
+  __syncwarp();
+}
+// Same tile also to the peers' copies of C (the fused halo all-gather): kept out of line of the single-GPU store above so that
+// the common path stays as lean as before (an in-loop peer branch cost 30-45 % on the plain GEMMs).
+__device__ __forceinline__ void warp_store_tile_peers(const float* st, const dgdm_gemm_params& p, int row0, int c0, int lane) {
+#pragma unroll 1
+  for (int it = 0; it < 8; ++it) {
+    int r = it * 4 + (lane >> 3), c = (lane & 7) * 4;
     if (row0 + r < p.M && c0 + c < p.N) {
+      const float4 t = *reinterpret_cast<const float4*>(st + r * TR_STRIDE + c);
       const size_t off = (size_t)(row0 + r) * p.ldc + c0 + c;
-      if (p.n_peers == 0) {
-        *reinterpret_cast<float4*>(p.C + off) = t;
-      } else if (p.peers_multicast) {
-        multimem_st4(p.C_peers[0] + off, t);
-      } else {
+      if (p.peers_multicast) multimem_st4(p.C_peers[0] + off, t);
+      else {
         *reinterpret_cast<float4*>(p.C + off) = t;
         for (int d = 0; d < p.n_peers; ++d) *reinterpret_cast<float4*>(p.C_peers[d] + off) = t;
       }
     }
   }
   __syncwarp();
+}
+template <bool PEERS>
+__device__ __forceinline__ void warp_store_out(float* st, const float* v, const dgdm_gemm_params& p, int row0, int c0, int lane) {
+  if (!PEERS) { warp_store_tile(st, v, p.C, p.ldc, row0, c0, p.M, p.N, lane); return; }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(st + lane * TR_STRIDE + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+  warp_store_tile_peers(st, p, row0, c0, lane);
 }
 // coalesced global load of a 32x32 tile -> thread-row-owned regs v[32]
 __device__ __forceinline__ void warp_load_tile(float* st, float* v, const float* G, int ldg, int row0, int c0,
@@ -140,6 +158,7 @@ __device__ __forceinline__ void lds_row32(const float* s, float* o) {
 
 // Row-wise epilogue of one 128-row tile by one epilogue warp (32 rows): thread = row, accumulator row in TMEM at t_row.
 // Every feature test is warp-uniform and hoisted out of the 32-element loops.
+template <bool PEERS>
 __device__ __forceinline__ void epilogue_rows(const dgdm_gemm_params& p, const EpiVec& ev, float* st, uint32_t t_row, int row0, int lane) {
   const int row = row0 + lane;
   const float inv_scale = 1.0f / p.a_scale;
@@ -161,7 +180,7 @@ __device__ __forceinline__ void epilogue_rows(const dgdm_gemm_params& p, const E
 #pragma unroll
       for (int j = 0; j < 32; ++j) dot = fmaf(v[j], t[j], dot);
     }
-    if (p.C != nullptr) warp_store_tile(st, v, p, row0, c0, lane);
+    if (p.C != nullptr) warp_store_out<PEERS>(st, v, p, row0, c0, lane);
   };
   auto normalise = [&](int c0, const float* g, const float* b, float mean, float rstd) {
     lds_row32(g + c0, t);
@@ -259,6 +278,7 @@ __device__ __forceinline__ void epilogue_rows(const dgdm_gemm_params& p, const E
   if (p.dot_out != nullptr && row < p.M) p.dot_out[row] = apply_act(dot + p.dot_b, p.dot_act);
 }
 
+template <bool PEERS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16x2_kernel(const dgdm_gemm_params p, const GemmSched sc) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -316,7 +336,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16x2_kernel(const dgdm_
       fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * GEMM_NCHUNK);
       if (tid == 0) TRACE_EVENT(2, t);
-      epilogue_rows(p, ev, st, t_row, tile * GEMM_BM + warp * 32, lane);
+      epilogue_rows<PEERS>(p, ev, st, t_row, tile * GEMM_BM + warp * 32, lane);
       if (tid == 0) TRACE_EVENT(3, t);
       fence_before();
       __syncwarp();
@@ -476,7 +496,8 @@ static int g_num_sms = 0;
 static int launch_gemm(const dgdm_gemm_params& p, long long plane_stride, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_f16x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_f16x2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_f16x2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM) != cudaSuccess)
       return DGDM_ERR_LAUNCH;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -493,7 +514,8 @@ static int launch_gemm(const dgdm_gemm_params& p, long long plane_stride, cudaSt
   sc.ntiles = (p.M + GEMM_BM - 1) / GEMM_BM;
   sc.w_plane_stride = plane_stride;
   const int grid = sc.ntiles < g_num_sms ? sc.ntiles : g_num_sms;
-  gemm_f16x2_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(p, sc);
+  if (p.n_peers > 0) gemm_f16x2_kernel<true><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(p, sc);
+  else gemm_f16x2_kernel<false><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(p, sc);
   DGDM_CHECK_LAUNCH();
   return DGDM_OK;
 }

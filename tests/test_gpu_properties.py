@@ -82,3 +82,52 @@ def test_batch_4x50k_encoder_and_attention_equal_per_graph(base_model):
         assert rel_err(hb[sl], a1)[0] < 3e-5                      # attention: the key-split count (accumulation chains) differs with the batch
     out = m(b)
     assert out["graph_embedding"].shape == (4, 128) and torch.isfinite(out["graph_embedding"]).all()
+
+
+def test_attention_100k_sampled_rows_vs_float64_dense():
+    """Full-size parity on SAMPLED query rows: the reference cannot form the 100k x 100k scores, but 96 rows of them fit anywhere —
+    softmax(q k^T / sqrt(hd) - |dp| / T) v in float64 (torch, on the device, as the checker) vs the tcgen05 kernel's rows.
+    Bar: 5e-5 max-scaled (the 1e-4 parity bar with margin; includes the capped tensor-core accumulation bias)."""
+    n, D, H, hd = 100000, 128, 8, 16
+    g = torch.Generator().manual_seed(17)
+    qkv = torch.randn(n, 3 * D, generator=g).to(DEV)
+    pos = torch.rand(n, 2, generator=g).to(DEV)
+    seg = torch.tensor([0, n], dtype=torch.int32, device=DEV)
+    out = ops.spatial_attention(qkv, pos, seg, 1, H, 0.8)
+    rows = torch.randint(0, n, (96,), generator=g).to(DEV)
+    q = qkv[rows, :D].double().view(-1, H, hd)
+    k = qkv[:, D:2 * D].double().view(n, H, hd)
+    v = qkv[:, 2 * D:].double().view(n, H, hd)
+    s = torch.einsum("rhd,nhd->rhn", q, k) / hd ** 0.5 - (torch.cdist(pos[rows].double(), pos.double()) / 0.8)[:, None, :]
+    ref = torch.einsum("rhn,nhd->rhd", torch.softmax(s, dim=-1), v).reshape(-1, D)
+    assert rel_err(out[rows], ref)[0] < 5e-5
+
+
+def test_encoder_layer_100k_sampled_rows_vs_float64():
+    """One DynamicGraphLayer (two GraphConvolutions + output projection + residual + LayerNorm) at 100k nodes / 1.6M edges:
+    sampled destination rows recomputed in float64 from the layer's own weights."""
+    from dgdm_histopath_lab_b200.core import DynamicGraphLayer
+    import torch.nn.functional as F
+    torch.manual_seed(3)
+    n, C = 100000, 128
+    d = synth.tile_graph(n, 8, seed=6)
+    ei = d.edge_index.to(DEV)
+    layer = DynamicGraphLayer(C, 32, C).to(DEV).eval()
+    x = torch.randn(n, C, generator=torch.Generator().manual_seed(4)).to(DEV)
+    out = layer(x, ei)
+    # float64 restatement on the device (dense ops over all nodes are cheap; only the comparison is sampled)
+    deg = torch.bincount(ei[1], minlength=n).double() + 1.0
+    dinv = deg.pow(-0.5)
+
+    def conv(conv_mod, h):
+        hl = h @ conv_mod.node_lin.weight.double().t()
+        msg = hl[ei[0]] * (dinv[ei[0]] * dinv[ei[1]])[:, None]
+        agg = torch.zeros(n, hl.size(1), dtype=torch.float64, device=DEV).index_add_(0, ei[1], msg) + hl * (dinv * dinv)[:, None]
+        return agg + conv_mod.bias.double()
+
+    h1 = F.gelu(conv(layer.graph_conv1, x.double()))
+    h2 = F.gelu(conv(layer.graph_conv2, h1))
+    y = h2 @ layer.output_proj.weight.double().t() + layer.output_proj.bias.double() + x.double()
+    ref = F.layer_norm(y, (C,), layer.norm1.weight.double(), layer.norm1.bias.double(), 1e-5)
+    rows = torch.randint(0, n, (4096,), generator=torch.Generator().manual_seed(5)).to(DEV)
+    assert rel_err(out[rows], ref[rows])[0] < 1e-5

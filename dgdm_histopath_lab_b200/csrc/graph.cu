@@ -74,6 +74,63 @@ __global__ void __launch_bounds__(256) order_rows_kernel(const long long* __rest
   }
 }
 
+// Multi-block exclusive scan (n beyond a few thousand): per-block sums -> one-block scan of the sums -> per-block rescan + offset.
+constexpr int SCAN_TILE = 2048;       // elements per block (1024 threads x 2)
+__device__ __forceinline__ int block_exclusive_scan_1024(int v, int* warp_tot /*[32] smem*/, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int s = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+  if (lane == 31) warp_tot[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_tot[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+    warp_tot[lane] = w;
+  }
+  __syncthreads();
+  total = warp_tot[31];
+  const int excl = (warp ? warp_tot[warp - 1] : 0) + s - v;
+  __syncthreads();
+  return excl;
+}
+__global__ void __launch_bounds__(1024) scan_block_sums_kernel(const int* __restrict__ in, int n, int* __restrict__ sums) {
+  __shared__ int wt[32];
+  const int i0 = blockIdx.x * SCAN_TILE + 2 * threadIdx.x;
+  int v = (i0 < n ? in[i0] : 0) + (i0 + 1 < n ? in[i0 + 1] : 0);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) wt[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int w = wt[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    if (threadIdx.x == 0) sums[blockIdx.x] = w;
+  }
+}
+__global__ void __launch_bounds__(1024) scan_apply_kernel(const int* __restrict__ in, int n, const int* __restrict__ offs /*exclusive, [nb+1]*/,
+                                                          int* __restrict__ out) {
+  __shared__ int wt[32];
+  const int i0 = blockIdx.x * SCAN_TILE + 2 * threadIdx.x;
+  const int a = i0 < n ? in[i0] : 0, b = i0 + 1 < n ? in[i0 + 1] : 0;
+  int total;
+  const int excl = block_exclusive_scan_1024(a + b, wt, total) + offs[blockIdx.x];
+  if (i0 < n) out[i0] = excl;
+  if (i0 + 1 < n) out[i0 + 1] = excl + a;
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = offs[gridDim.x];
+}
+// out[0..n] = exclusive scan of in[0..n); scratch: >= n / SCAN_TILE + 2 ints (NULL or too small -> single-block scan)
+static void launch_exclusive_scan(const int* in, int* out, int n, int* scratch, int scratch_ints, cudaStream_t s) {
+  const int nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (nb <= 2 || scratch == nullptr || scratch_ints < 2 * (nb + 1)) { exclusive_scan_kernel<<<1, 1024, 0, s>>>(in, out, n); return; }
+  int* sums = scratch; int* offs = scratch + (nb + 1);
+  scan_block_sums_kernel<<<nb, 1024, 0, s>>>(in, n, sums);
+  exclusive_scan_kernel<<<1, 1024, 0, s>>>(sums, offs, nb);
+  scan_apply_kernel<<<nb, 1024, 0, s>>>(in, n, offs, out);
+}
+
 // ------------------------------------------------------------------------------------------ SpMM
 template <int VPL>
 __global__ void __launch_bounds__(256) spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
@@ -169,69 +226,93 @@ __global__ void __launch_bounds__(256) radix_hist_kernel(const float* __restrict
   __syncthreads();
   if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
-__global__ void radix_pick_kernel(unsigned* __restrict__ state, unsigned* __restrict__ hist) {
-  if (threadIdx.x == 0) {
-    unsigned k = state[1];
+__global__ void __launch_bounds__(256) radix_pick_kernel(unsigned* __restrict__ state, unsigned* __restrict__ hist) {
+  // digit d* = the largest d with suffix[d] = sum_{d' >= d} hist[d'] >= k (k-th largest lies in it); 256 threads, reverse inclusive scan
+  __shared__ unsigned suf[256];
+  const int d = threadIdx.x;
+  suf[d] = hist[255 - d];                       // reversed: index r = 255 - d
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {
+    const unsigned t = d >= o ? suf[d - o] : 0u;
+    __syncthreads();
+    suf[d] += t;
+    __syncthreads();
+  }
+  const unsigned k = state[1];
+  // suf[r] = sum of hist over digits >= 255 - r; the wanted digit is the smallest r with suf[r] >= k
+  const bool here = suf[d] >= k && (d == 0 || suf[d - 1] < k);
+  __syncthreads();
+  if (here) {
     const int shift = 24 - 8 * (int)state[2];
-    int d = 255;
-    for (; d > 0; --d) { if (hist[d] >= k) break; k -= hist[d]; }
-    state[0] |= ((unsigned)d << shift);
-    state[1] = k;                       // how many elements with this digit (finally: equal to the threshold) to take
+    state[0] |= ((unsigned)(255 - d) << shift);
+    state[1] = k - (d == 0 ? 0u : suf[d - 1]);  // how many elements with this digit (finally: equal to the threshold) to take
     state[2] += 1;
   }
-  __syncthreads();
   hist[threadIdx.x] = 0;
 }
-// one block: ordered compaction. selected = key > T, or key == T for the first state[1] such nodes (lowest index first)
-__global__ void __launch_bounds__(1024) topk_compact_kernel(const float* __restrict__ s, int N, const unsigned* __restrict__ state,
-                                                            int* __restrict__ perm, int* __restrict__ node_map) {
-  __shared__ int wsel[32], weq[32];
-  __shared__ int carry_sel, carry_eq;
-  if (threadIdx.x == 0) { carry_sel = 0; carry_eq = 0; }
+// Ordered compaction, multi-block. selected = key > T, or key == T for the first state[1] such nodes (lowest index first).
+// (a) per-block counts of (key > T, key == T); (b) one block turns them into exclusive offsets of the ties and of the selected
+// nodes; (c) every block re-derives its local prefixes and writes perm / node_map.
+constexpr int TOPK_TILE = 1024;
+__global__ void __launch_bounds__(1024) topk_count_kernel(const float* __restrict__ s, int N, const unsigned* __restrict__ state,
+                                                          int* __restrict__ blk_gt, int* __restrict__ blk_eq) {
+  __shared__ int wg[32], we[32];
+  const unsigned T = state[0];
+  const int i = blockIdx.x * TOPK_TILE + threadIdx.x;
+  unsigned key = 0; const bool valid = i < N;
+  if (valid) key = float_to_ordered(s[i]);
+  int g = valid && key > T, e = valid && key == T;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { g += __shfl_xor_sync(0xffffffffu, g, o); e += __shfl_xor_sync(0xffffffffu, e, o); }
+  if ((threadIdx.x & 31) == 0) { wg[threadIdx.x >> 5] = g; we[threadIdx.x >> 5] = e; }
   __syncthreads();
+  if (threadIdx.x < 32) {
+    g = wg[threadIdx.x]; e = we[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { g += __shfl_xor_sync(0xffffffffu, g, o); e += __shfl_xor_sync(0xffffffffu, e, o); }
+    if (threadIdx.x == 0) { blk_gt[blockIdx.x] = g; blk_eq[blockIdx.x] = e; }
+  }
+}
+__global__ void __launch_bounds__(1024) topk_offsets_kernel(const int* __restrict__ blk_gt, const int* __restrict__ blk_eq, int nb,
+                                                            const unsigned* __restrict__ state, int* __restrict__ eq_off,
+                                                            int* __restrict__ sel_off) {
+  __shared__ int wt[32];
+  __shared__ int carry_eq, carry_sel;
+  if (threadIdx.x == 0) { carry_eq = 0; carry_sel = 0; }
+  __syncthreads();
+  const int need_eq = (int)state[1];
+  for (int base = 0; base < nb; base += 1024) {
+    const int b = base + threadIdx.x;
+    const int e = b < nb ? blk_eq[b] : 0;
+    int tot_e;
+    const int eo = block_exclusive_scan_1024(e, wt, tot_e) + carry_eq;
+    int take = need_eq - eo; take = take < 0 ? 0 : (take > e ? e : take);
+    const int sel = b < nb ? blk_gt[b] + take : 0;
+    int tot_s;
+    const int so = block_exclusive_scan_1024(sel, wt, tot_s) + carry_sel;
+    if (b < nb) { eq_off[b] = eo; sel_off[b] = so; }
+    __syncthreads();
+    if (threadIdx.x == 0) { carry_eq += tot_e; carry_sel += tot_s; }
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(1024) topk_scatter_kernel(const float* __restrict__ s, int N, const unsigned* __restrict__ state,
+                                                            const int* __restrict__ eq_off, const int* __restrict__ sel_off,
+                                                            int* __restrict__ perm, int* __restrict__ node_map) {
+  __shared__ int wt[32];
   const unsigned T = state[0];
   const int need_eq = (int)state[1];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int base = 0; base < N; base += 1024) {
-    const int i = base + threadIdx.x;
-    unsigned key = 0; bool valid = i < N;
-    if (valid) key = float_to_ordered(s[i]);
-    const int eq = valid && key == T;
-    // exclusive prefix of eq within the block
-    int e = eq;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, e, o); if (lane >= o) e += t; }
-    if (lane == 31) weq[warp] = e;
-    __syncthreads();
-    if (warp == 0) {
-      int w = weq[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
-      weq[lane] = w;
-    }
-    __syncthreads();
-    const int eq_before = carry_eq + (warp ? weq[warp - 1] : 0) + e - eq;
-    const int sel = valid && (key > T || (eq && eq_before < need_eq));
-    int p = sel;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, p, o); if (lane >= o) p += t; }
-    if (lane == 31) wsel[warp] = p;
-    __syncthreads();
-    if (warp == 0) {
-      int w = wsel[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
-      wsel[lane] = w;
-    }
-    __syncthreads();
-    const int pos = carry_sel + (warp ? wsel[warp - 1] : 0) + p - sel;
-    if (valid) {
-      node_map[i] = sel ? pos : -1;
-      if (sel) perm[pos] = i;
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) { carry_sel += wsel[31]; carry_eq += weq[31]; }
-    __syncthreads();
+  const int i = blockIdx.x * TOPK_TILE + threadIdx.x;
+  unsigned key = 0; const bool valid = i < N;
+  if (valid) key = float_to_ordered(s[i]);
+  const int eq = valid && key == T;
+  int tot;
+  const int eq_before = eq_off[blockIdx.x] + block_exclusive_scan_1024(eq, wt, tot);
+  const int sel = valid && (key > T || (eq && eq_before < need_eq));
+  const int pos = sel_off[blockIdx.x] + block_exclusive_scan_1024(sel, wt, tot);
+  if (valid) {
+    node_map[i] = sel ? pos : -1;
+    if (sel) perm[pos] = i;
   }
 }
 __global__ void init_select_state_kernel(unsigned* state, unsigned* hist, int k) {
@@ -347,7 +428,7 @@ extern "C" int dgdm_csr_build(const int64_t* edge_index, int E, int N, int* rowp
   if (cudaMemsetAsync(cnt, 0, sizeof(int) * 2 * (N + 1), s) != cudaSuccess) return DGDM_ERR_LAUNCH;
   const long long* ei = (const long long*)edge_index;
   if (E > 0) count_dst_kernel<<<grid1d(E), 256, 0, s>>>(ei, E, cnt);
-  exclusive_scan_kernel<<<1, 1024, 0, s>>>(cnt, rowptr, N);
+  launch_exclusive_scan(cnt, rowptr, N, tmp_eid, E + 16, s);      // tmp_eid is free until fill_unordered_kernel
   dinv_kernel<<<grid1d(N), 256, 0, s>>>(rowptr, N, dinv);
   if (E > 0) {
     fill_unordered_kernel<<<grid1d(E), 256, 0, s>>>(ei, E, rowptr, cursor, tmp_eid);
@@ -390,7 +471,7 @@ extern "C" int dgdm_edge_attr_aggregate(const int* rowptr, const int* eid, const
   return DGDM_OK;
 }
 
-extern "C" size_t dgdm_topk_pool_work_ints(int N) { return (size_t)N + 512; }
+extern "C" size_t dgdm_topk_pool_work_ints(int N) { return (size_t)N + 512 + 4 * ((size_t)N / TOPK_TILE + 2); }
 
 extern "C" int dgdm_topk_select(const float* scores, int N, int k, int* perm, int* node_map, int* work, void* stream) {
   if (!scores || !perm || !node_map || !work || N <= 0 || k <= 0 || k > N) return DGDM_ERR_INVALID;
@@ -401,7 +482,12 @@ extern "C" int dgdm_topk_select(const float* scores, int N, int k, int* perm, in
     radix_hist_kernel<<<grid1d(N, 256, 148 * 4), 256, 0, s>>>(scores, N, state, hist);
     radix_pick_kernel<<<1, 256, 0, s>>>(state, hist);
   }
-  topk_compact_kernel<<<1, 1024, 0, s>>>(scores, N, state, perm, node_map);
+  const int nb = (N + TOPK_TILE - 1) / TOPK_TILE;
+  int* blk = work + 512;                 // [gt | eq | eq_off | sel_off], nb + 1 ints each (the state / histogram use the first 264 ints)
+  int* blk_gt = blk; int* blk_eq = blk + (nb + 1); int* eq_off = blk + 2 * (nb + 1); int* sel_off = blk + 3 * (nb + 1);
+  topk_count_kernel<<<nb, 1024, 0, s>>>(scores, N, state, blk_gt, blk_eq);
+  topk_offsets_kernel<<<1, 1024, 0, s>>>(blk_gt, blk_eq, nb, state, eq_off, sel_off);
+  topk_scatter_kernel<<<nb, 1024, 0, s>>>(scores, N, state, eq_off, sel_off, perm, node_map);
   DGDM_CHECK_LAUNCH();
   return DGDM_OK;
 }
@@ -421,7 +507,7 @@ extern "C" int dgdm_csr_pool(const int* rowptr, const int* col, int N, const int
   cudaStream_t s = (cudaStream_t)stream;
   int* cnt = work;
   csr_pool_count_kernel<<<(k + 7) / 8, 256, 0, s>>>(rowptr, col, perm, node_map, k, cnt, p_dinv);
-  exclusive_scan_kernel<<<1, 1024, 0, s>>>(cnt, p_rowptr, k);
+  launch_exclusive_scan(cnt, p_rowptr, k, work + k + 8, (k / SCAN_TILE + 2) * 2 + 8, s);
   csr_pool_fill_kernel<<<(k + 7) / 8, 256, 0, s>>>(rowptr, col, perm, node_map, k, p_rowptr, p_dinv, p_col, p_norm);
   DGDM_CHECK_LAUNCH();
   return DGDM_OK;

@@ -17,8 +17,8 @@ class KernelError(RuntimeError):
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim; memsets not counted)
 KERNELS_PER_CALL = {
-    "dgdm_gemm_f16x2": 1, "dgdm_gemm_simt": 2, "dgdm_split_weight_f16": 1, "dgdm_rowwise_epilogue": 1, "dgdm_csr_build": 5,
-    "dgdm_spmm_gcn": 1, "dgdm_edge_attr_aggregate": 1, "dgdm_topk_select": 10, "dgdm_pool_gather": 1, "dgdm_csr_pool": 3,
+    "dgdm_gemm_f16x2": 1, "dgdm_gemm_simt": 2, "dgdm_split_weight_f16": 1, "dgdm_rowwise_epilogue": 1, "dgdm_csr_build": 7,
+    "dgdm_spmm_gcn": 1, "dgdm_edge_attr_aggregate": 1, "dgdm_topk_select": 12, "dgdm_pool_gather": 1, "dgdm_csr_pool": 5,
     "dgdm_unpool_add_act": 1, "dgdm_segment_softmax_scores": 1, "dgdm_segment_minmax": 1, "dgdm_spatial_pe_add": 1,
     "dgdm_spatial_attention": 6, "dgdm_spatial_attention_weights": 1, "dgdm_attention_pool": 2, "dgdm_diffusion_add_noise": 1,
     "dgdm_groupnorm_silu": 1, "dgdm_ddpm_update": 1, "dgdm_validate_inputs": 1, "dgdm_knn_cosine": 4, "dgdm_knn2d": 2,
@@ -267,7 +267,7 @@ def csr_pool(csr, perm, node_map):
     p_col = torch.empty(max(csr.E, 1), dtype=torch.int32, device=dev)
     p_norm = torch.empty(max(csr.E, 1), dtype=torch.float32, device=dev)
     p_dinv = torch.empty(k, dtype=torch.float32, device=dev)
-    work = torch.empty(k + 64, dtype=torch.int32, device=dev)
+    work = torch.empty(k + 2 * (k // 2048 + 2) + 64, dtype=torch.int32, device=dev)      # counts + scan scratch
     _check(lib.dgdm_csr_pool(_p(csr.rowptr), _p(csr.col), csr.N, _p(perm), _p(node_map), k, _p(p_rowptr), _p(p_col),
                              _p(p_norm), _p(p_dinv), _p(work), _stream()), "dgdm_csr_pool")
     return CSR(p_rowptr, p_col, None, p_norm, p_dinv, k, csr.E)   # E is an upper bound; the true count is rowptr[k]

@@ -230,11 +230,21 @@ __global__ void __launch_bounds__(256) validate_kernel(const float* __restrict__
   float amax = 0.f, s = 0.f, ss = 0.f;
   int fnan = 0, finf = 0, fhi = 0, flo = 0;
   const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (size_t i = t0; i < n_x; i += stride) {
-    const float v = x[i];
+  auto take = [&](float v) {
     if (isnan(v)) fnan = 1; else if (isinf(v)) finf = 1;
     else { amax = fmaxf(amax, fabsf(v)); s += v; ss = fmaf(v, v, ss); }
+  };
+  // 128-bit loads, four in flight per thread (x is 16-byte aligned: torch allocations are); scalar tail
+  const size_t n4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? n_x / 4 : 0;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  size_t i = t0;
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    const float4 a = __ldg(x4 + i), b = __ldg(x4 + i + stride), c = __ldg(x4 + i + 2 * stride), d = __ldg(x4 + i + 3 * stride);
+    take(a.x); take(a.y); take(a.z); take(a.w); take(b.x); take(b.y); take(b.z); take(b.w);
+    take(c.x); take(c.y); take(c.z); take(c.w); take(d.x); take(d.y); take(d.z); take(d.w);
   }
+  for (; i < n4; i += stride) { const float4 a = __ldg(x4 + i); take(a.x); take(a.y); take(a.z); take(a.w); }
+  for (size_t j = 4 * n4 + t0; j < n_x; j += stride) take(x[j]);
   for (size_t i = t0; i < n_ei; i += stride) {
     const long long v = ei[i];
     if (v > (long long)N - 1) fhi = 1;

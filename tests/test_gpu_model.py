@@ -306,3 +306,19 @@ def test_non_default_activation_and_pooling_options_vs_oracle(activation, poolin
     out = m.to(DEV)(b.to(DEV), return_embeddings=True)
     assert rel_err(out["node_embeddings"], ref["node_embeddings"])[0] < 1e-4
     assert rel_err(out["graph_embedding"], ref["graph_embedding"])[0] < 1e-4
+
+
+@pytest.mark.parametrize("n,e", [(1, 0), (2, 1), (3, 0), (9, 20), (33, 100), (129, 7)])
+def test_tiny_and_degenerate_graphs_vs_oracle(n, e):
+    """Edge cases of the graph container: a single node, no edges at all, fewer nodes than a warp / a tile, more pooling levels
+    than nodes (k = max(1, int(0.5 n)) bottoms out at 1), duplicate edges and self loops as drawn."""
+    m = make_model(SMALL_CFG)
+    g = torch.Generator().manual_seed(100 + n)
+    x = torch.randn(n, 48, generator=g)
+    ei = torch.randint(0, n, (2, e), generator=g) if e > 0 else torch.empty(2, 0, dtype=torch.long)
+    pos = torch.rand(n, 2, generator=g)
+    ref = O.dgdm_forward(sd_cpu(m), oracle_cfg(SMALL_CFG), x, ei, None, None, pos)
+    out = m.to(DEV)(Data(x=x.to(DEV), edge_index=ei.to(DEV), pos=pos.to(DEV)), return_embeddings=True)
+    assert out["node_embeddings"].shape == (n, 32)
+    assert rel_err(out["node_embeddings"], ref["node_embeddings"])[0] < 1e-4
+    assert rel_err(out["graph_embedding"], ref["graph_embedding"])[0] < 1e-4

@@ -24,6 +24,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BASE_CFG = dict(node_features=768, hidden_dims=[512, 256, 128], num_diffusion_steps=10, attention_heads=8, graph_layers=4)
+LARGE_CFG = dict(node_features=1024, hidden_dims=[768, 512, 256, 128], num_diffusion_steps=20, attention_heads=16, graph_layers=6)
 METRIC = "DGDM fwd nodes/sec (100k-node graph)"
 
 
@@ -135,8 +136,9 @@ def main():
     ap.add_argument("--ref-nodes", type=int, default=2000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="graph100k", choices=["graph100k", "batch4x50k"],
-                    help="graph100k = BASELINE.json's metric (one 100k-node tile graph); batch4x50k = configs[1] (4 x 50k-node graphs in one Batch)")
+    ap.add_argument("--workload", default="graph100k", choices=["graph100k", "batch4x50k", "large"],
+                    help="graph100k = BASELINE.json's metric (one 100k-node tile graph); batch4x50k = configs[1] (4 x 50k-node graphs in one Batch); "
+                         "large = configs[3]: DGDM-Large (configs/dgdm_large.yaml) on one --nodes graph (500000 in BASELINE.json), meant for torchrun")
     ap.add_argument("--no-fused-halo", action="store_true", help="multi-GPU: NCCL all-gather per propagate instead of the GEMM-epilogue P2P/multicast stores")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -160,14 +162,15 @@ def main():
 
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        model = DGDMModel(**BASE_CFG).eval()
+        model = DGDMModel(**(LARGE_CFG if args.workload == "large" else BASE_CFG)).eval()
     model.load_state_dict(synth.seeded_state_dict(model, 0))
     model = model.to(dev)
+    feat = LARGE_CFG["node_features"] if args.workload == "large" else 768
     if args.workload == "batch4x50k":
         from dgdm_histopath_lab_b200 import Batch
         host = Batch.from_data_list([synth.tile_graph(args.nodes // 2, 768, seed=100 + i) for i in range(4)])
     else:
-        host = synth.tile_graph(args.nodes, 768, seed=1234)
+        host = synth.tile_graph(args.nodes, feat, seed=1234)
     N, E = host.x.size(0), host.edge_index.size(1)
     host_batch = getattr(host, "batch", None)
     rows = None
@@ -224,7 +227,7 @@ def main():
         if host_batch is not None:
             hg.batch = host_batch.pin_memory()
         nx = N if rows is None else rows[1] - rows[0]
-        h2d = nx * 768 * 4 + hg.edge_index.numel() * 8 + hg.pos.numel() * 4
+        h2d = nx * feat * 4 + hg.edge_index.numel() * 8 + hg.pos.numel() * 4
 
         def run_e2e(k):
             g = None
@@ -256,10 +259,12 @@ def main():
     gemm_ms = prof.get("dgdm_gemm_f16x2", [0, 0.0])[1]
     nq = N if world == 1 else -(-N // world)
     att_flops = 4.0 * nq * N * 128 + 0.0                                      # QK^T + PV, per rank (query rows sharded)
-    att_exp = 8.0 * nq * N
+    n_heads = 16 if args.workload == "large" else 8
+    att_exp = float(n_heads) * nq * N
     spmm_bytes = sum((e + n) * c * 4 + n * c * 4 + (e + n) * 8 + (n + 1) * 4 for (n, e, c) in meta.get("spmm", []))
     gemm_flops = sum(2.0 * m * k * n_ for (m, k, n_) in meta.get("gemm", []))
-    roof = {"kernel": "spatial_attn_tc_kernel (+ prep / combine kernels of the same dgdm_spatial_attention call)", "bound": "tensor", "achieved": att_flops / (att_ms * 1e-3) / 1e12 if att_ms else None,
+    roof = {"kernel": ("attn_simt_kernel<8> (exact fp32 CUDA-core path, DGDM-Large head_dim 8)" if args.workload == "large" else
+                       "spatial_attn_tc_kernel (+ prep / combine kernels of the same dgdm_spatial_attention call)"), "bound": "tensor", "achieved": att_flops / (att_ms * 1e-3) / 1e12 if att_ms else None,
             "peak": pk["tf_sustained"], "unit": "TFLOP/s", "traffic": None, "peak_source": pk["src"],
             "note": "dominant kernel; exp2(MUFU)-bound, not tensor- or HBM-bound: head_dim 16 gives K=16 / N=16 MMAs",
             "gexp_per_s": att_exp / (att_ms * 1e-3) / 1e9 if att_ms else None, "ms": att_ms}
@@ -268,8 +273,9 @@ def main():
     sm_clock_ghz = ((clocks or {}).get("sm_mhz") or 1965) / 1e3
     mufu_peak = 148 * 16 * sm_clock_ghz                      # G ops/s at the SM clock sampled during the run
     if att_ms:
-        roof["mufu"] = {"achieved_gops": 1.25 * att_exp / (att_ms * 1e-3) / 1e9, "peak_gops": mufu_peak,
-                        "frac": 1.25 * att_exp / (att_ms * 1e-3) / 1e9 / mufu_peak, "ops_per_score": 1.25}
+        mops = 2.0 if args.workload == "large" else 1.25       # the CUDA-core kernel recomputes the distance per head
+        roof["mufu"] = {"achieved_gops": mops * att_exp / (att_ms * 1e-3) / 1e9, "peak_gops": mufu_peak,
+                        "frac": mops * att_exp / (att_ms * 1e-3) / 1e9 / mufu_peak, "ops_per_score": 1.25 if args.workload != "large" else 2.0}
     roof["frac"] = roof["achieved"] / roof["peak"] if roof["achieved"] else None
     roof["traffic"], roof["traffic_source"] = ncu_traffic("spatial_attn_tc_kernel")
     roof_hbm = {"kernel": "spmm_gcn_kernel (all launches)", "bound": "hbm", "achieved": spmm_bytes / (spmm_ms * 1e-3) / 1e9 if spmm_ms else None,
@@ -292,6 +298,8 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": (f"DGDM-Base forward (eval, inference mode, return_embeddings) on one synthetic {N}-node 768-d tile graph, "
                                         f"E={E} directed edges, random-init seeded weights") if args.workload == "graph100k" else
+                                       (f"DGDM-Large forward (1024-d nodes, hidden [768,512,256,128], 16 heads, 6 layers) on one synthetic {N}-node "
+                                        f"tile graph (configs[3]), E={E} directed edges") if args.workload == "large" else
                                        (f"DGDM-Base forward on a Batch of 4 synthetic {N // 4}-node 768-d tile graphs (configs[1]), E={E} directed edges"),
                            "nodes": N, "edges": E,
                            "l2_policy": "inputs larger than L2 (x = 307 MB, activations > 200 MB per layer)",

@@ -383,7 +383,7 @@ class MultiHeadAttention(nn.Module):
             kseg = torch.tensor([0, Lk], dtype=torch.int32, device=dev)
             if self.head_dim not in (4, 8, 16, 32, 64):
                 raise NotImplementedError(f"head_dim {self.head_dim}: supported head widths are 4, 8, 16, 32, 64")
-            o = ops.spatial_attention(qkv, None, qseg, 1, self.num_heads, kv_qkv=kv_qkv, kseg_ptr=kseg)
+            o = ops.spatial_attention_any(qkv, None, qseg, 1, self.num_heads, kv_qkv=kv_qkv if kv_qkv is not qkv else None, kseg_ptr=kseg)
             o = ops.linear(o, split_weight(self.out_proj.weight), self.out_proj.bias.detach() if self.out_proj.bias is not None else None)
             outs.append(o)
             if need_weights:
@@ -435,7 +435,7 @@ class SpatialAttention(nn.Module):
         if part is None:
             xp = ops.spatial_pe_add(x, pos, seg_ptr, num_seg)
             qkv = ops.linear(xp, w, bias)
-            o = ops.spatial_attention(qkv, pos, seg_ptr, num_seg, self.num_heads, self.temperature, max_seg=max_seg)
+            o = ops.spatial_attention_any(qkv, pos, seg_ptr, num_seg, self.num_heads, self.temperature, max_seg=max_seg)
         else:
             if need_weights:
                 raise NotImplementedError("return_attention is not available for node-partitioned graphs")
@@ -444,8 +444,8 @@ class SpatialAttention(nn.Module):
             xp = ops.spatial_pe_add(x, pos_l, qseg, num_seg, minmax_from=(pos, seg_ptr))
             qkv = ops.linear(xp, w, bias)
             qkv_full = part.gather(qkv)
-            o = ops.spatial_attention(qkv, pos_l, qseg, num_seg, self.num_heads, self.temperature,
-                                      kv_qkv=qkv_full, kv_pos=pos, kseg_ptr=seg_ptr, max_seg=max_seg)
+            o = ops.spatial_attention_any(qkv, pos_l, qseg, num_seg, self.num_heads, self.temperature,
+                                          kv_qkv=qkv_full, kv_pos=pos, kseg_ptr=seg_ptr, max_seg=max_seg)
         out = ops.linear(o, split_weight(att.out_proj.weight), att.out_proj.bias.detach(), r_pre=x, ln1=_ln(self.norm))
         weights = None
         if need_weights:

@@ -333,6 +333,40 @@ def spatial_attention(qkv, pos, seg_ptr, num_seg, heads, temperature=1.0, *, kv_
     return out
 
 
+def spatial_attention_any(qkv, pos, seg_ptr, num_seg, heads, temperature=1.0, *, kv_qkv=None, kv_pos=None, kseg_ptr=None, max_seg=0):
+    """spatial_attention for any supported head width. head_dim 16 goes straight to the kernels. Narrower heads whose width divides
+    16 (DGDM-Large: 16 heads x 8) run on the SAME tcgen05 kernel: every head is zero-padded to 16 dims (dot products unchanged),
+    q is pre-scaled by sqrt(16/hd) so that the kernel's 1/sqrt(16) becomes 1/sqrt(hd), and the heads go through in groups of 8
+    (one 128-wide launch per group) — ~5x faster than the exact CUDA-core kernel, same fp32-class split arithmetic."""
+    N, D3 = qkv.shape
+    D = D3 // 3
+    hd = D // heads
+    if hd == 16 or 16 % hd != 0 or heads % 8 != 0 or hd > 16:
+        return spatial_attention(qkv, pos, seg_ptr, num_seg, heads, temperature, kv_qkv=kv_qkv, kv_pos=kv_pos, kseg_ptr=kseg_ptr, max_seg=max_seg)
+    kvq = qkv if kv_qkv is None else kv_qkv
+    out = torch.empty(N, D, dtype=torch.float32, device=qkv.device)
+    qs = (16.0 / hd) ** 0.5
+
+    def padded(src, col0, scale):             # [n, 8*hd] columns col0.. of src -> [n, 128] with each head padded to 16 dims
+        n = src.size(0)
+        t = src.new_zeros(n, 8, 16)
+        t[:, :, :hd] = src[:, col0:col0 + 8 * hd].reshape(n, 8, hd)
+        return (t * scale if scale != 1.0 else t).reshape(n, 128)
+
+    for g in range(heads // 8):
+        c0 = g * 8 * hd
+        k_p, v_p = padded(kvq, D + c0, 1.0), padded(kvq, 2 * D + c0, 1.0)
+        q_p = padded(qkv, c0, qs)
+        if kv_qkv is None:
+            o = spatial_attention(torch.cat([q_p, k_p, v_p], 1), pos, seg_ptr, num_seg, 8, temperature, max_seg=max_seg)
+        else:
+            qq = torch.cat([q_p, q_p.new_zeros(N, 256)], 1)          # only the q third of the query-side matrix is read
+            kk = torch.cat([k_p.new_zeros(kvq.size(0), 128), k_p, v_p], 1)
+            o = spatial_attention(qq, pos, seg_ptr, num_seg, 8, temperature, kv_qkv=kk, kv_pos=kv_pos, kseg_ptr=kseg_ptr, max_seg=max_seg)
+        out[:, c0:c0 + 8 * hd] = o.reshape(N, 8, 16)[:, :, :hd].reshape(N, 8 * hd)
+    return out
+
+
 def spatial_attention_weights(qkv, pos, heads, temperature=1.0):
     lib = _lib.load()
     n, D3 = qkv.shape

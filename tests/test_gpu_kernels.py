@@ -188,6 +188,24 @@ def test_spatial_attention_other_head_dims_exact_fp32_kernel(D, H, precise):
     assert rel_err(out, torch.cat(refs))[0] < 3e-6
 
 
+def test_spatial_attention_head_dim_8_on_tensor_cores_via_zero_padding():
+    """DGDM-Large shape (16 heads x 8 over D = 128): heads zero-padded to 16 dims and run through the tcgen05 kernel in two
+    8-head launches (ops.spatial_attention_any) vs a float64 dense softmax, also with separate (all-gathered) keys/values."""
+    g = _gen(88)
+    n, D, H, hd = 700, 128, 16, 8
+    qkv = torch.randn(n, 3 * D, generator=g); pos = torch.rand(n, 2, generator=g)
+    q, k, v = (qkv[:, i * D:(i + 1) * D].double().view(n, H, hd).transpose(0, 1) for i in range(3))
+    ref = (torch.softmax(q @ k.transpose(1, 2) / hd ** 0.5 - torch.cdist(pos.double(), pos.double()), -1) @ v).transpose(0, 1).reshape(n, D)
+    seg = torch.tensor([0, n], dtype=torch.int32, device=DEV)
+    out = ops.spatial_attention_any(qkv.to(DEV), pos.to(DEV), seg, 1, H, 1.0)
+    assert rel_err(out, ref)[0] < 2e-5
+    # query rows 200..450 against all keys (the node-partitioned call pattern)
+    qseg = torch.tensor([0, 250], dtype=torch.int32, device=DEV)
+    out2 = ops.spatial_attention_any(qkv[200:450].to(DEV), pos[200:450].to(DEV).contiguous(), qseg, 1, H, 1.0,
+                                     kv_qkv=qkv.to(DEV), kv_pos=pos.to(DEV), kseg_ptr=seg)
+    assert rel_err(out2, ref[200:450])[0] < 2e-5
+
+
 def test_spatial_attention_large_scores_trigger_rescale():
     g = _gen(10)
     n, D, H = 700, 128, 8

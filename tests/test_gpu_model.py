@@ -110,6 +110,41 @@ def test_builder_edges_exact_vs_golden_and_oracle():
     assert np.array_equal(gph.pos.numpy(), g["pos"])
 
 
+def test_node_partitioned_batch_of_graphs_matches_single_gpu():
+    """a Batch of 3 graphs (segments cut by the rank boundaries) through the node-partitioned forward, 2 in-process ranks"""
+    import copy
+    import threading
+    from dgdm_histopath_lab_b200.parallel import ThreadComm, even_bounds
+    cfg = dict(node_features=64, hidden_dims=[128, 64, 128], num_diffusion_steps=10, attention_heads=8, graph_layers=3, num_classes=2)
+    m = make_model(cfg).to(DEV)
+    b = Batch.from_data_list([synth.tile_graph(k, 64, seed=30 + i) for i, k in enumerate((500, 330, 700))]).to(DEV)
+    n = b.x.size(0)
+    ref = m(b, return_embeddings=True)
+    torch.cuda.synchronize()
+    comms, bounds = ThreadComm.make(2), even_bounds(n, 2)
+    outs, errs = [None] * 2, [None] * 2
+
+    def run(r):
+        try:
+            mr = copy.deepcopy(m)
+            mr.set_partition(comms[r])
+            dr = Data(x=b.x[bounds[r]:bounds[r + 1]].contiguous(), edge_index=b.edge_index, pos=b.pos, num_nodes=n)
+            dr.batch = b.batch
+            outs[r] = mr(dr, return_embeddings=True)
+            torch.cuda.synchronize()
+        except Exception as e:
+            errs[r] = e
+            comms[r]._sh["bar"].abort()
+
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    [t.start() for t in ts]
+    [t.join(120) for t in ts]
+    assert all(e is None for e in errs), errs
+    emb = torch.cat([o["node_embeddings"] for o in outs], 0)
+    assert rel_err(emb, ref["node_embeddings"])[0] < 2e-5
+    assert outs[0]["graph_embedding"].shape == (3, 128) and rel_err(outs[1]["graph_embedding"], ref["graph_embedding"])[0] < 2e-5
+
+
 @pytest.mark.parametrize("world,n", [(2, 1500), (3, 1001)])
 def test_node_partitioned_forward_matches_single_gpu(world, n):
     """The node-partitioned forward (parallel.py: halo all-gather per propagate, context-parallel attention, replicated exact

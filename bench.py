@@ -157,9 +157,19 @@ def main():
     ops.device_check(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # stdout carries exactly one JSON line (NCCL prints its version banner there)
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout must carry exactly ONE JSON line: NCCL prints its version banner to fd 1 when the first communicator is created,
+        # so fd 1 points at stderr while the process group comes up
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")

@@ -47,8 +47,8 @@ SIGNATURES = {
     "dgdm_topk_pool_work_ints": (c_size_t, [c_int]),
     "dgdm_topk_select": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dgdm_pool_gather": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
-    "dgdm_csr_pool": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                              c_void_p, c_void_p]),
+    "dgdm_csr_pool": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_void_p]),
     "dgdm_unpool_add_act": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "dgdm_segment_softmax_scores": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                             c_void_p, c_void_p]),
@@ -58,6 +58,9 @@ SIGNATURES = {
     "dgdm_spatial_attention": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                        c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "dgdm_spatial_attention_weights": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "dgdm_mha_dense": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                               C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, c_void_p, c_void_p, c_void_p, c_int, c_float,
+                               c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "dgdm_attention_pool_work_floats": (c_size_t, [c_int, c_int, c_int, c_int]),
     "dgdm_attention_pool": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dgdm_diffusion_add_noise": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -32,7 +32,15 @@ class _IdCache:
 
 
 _SPLIT_CACHE = _IdCache()
-_CAT_CACHE = {}
+_CAT_CACHE = _IdCache()
+
+
+def invalidate_weight_cache():
+    """Drop every cached fp16 weight image. The caches re-make an image when a Parameter's storage address or `_version`
+    changes (optimizer steps, load_state_dict, .to()); an in-place write through `param.data` changes neither and must be
+    followed by this call."""
+    for c in (_SPLIT_CACHE, _CAT_CACHE, _COLSPLIT_CACHE, _SCALAR_CACHE):
+        c._d.clear()
 
 
 def split_weight(param):
@@ -46,13 +54,18 @@ def split_weight(param):
 
 
 def split_weight_cat(params, tag):
-    """Planes of torch.cat(params) (e.g. q|k|v projection) cached on the identity/version of all parts."""
+    """Planes of torch.cat(params) (e.g. q|k|v projection). The entry lives in a per-tag dict attached to the first part
+    (dies with it) and is valid only while every part is the SAME object at the same address / version."""
     key = tuple((p.data_ptr(), p._version) for p in params)
-    hit = _CAT_CACHE.get((tag, id(params[0])))
-    if hit is None or hit[0] != key:
+    per_tag = _CAT_CACHE.get(params[0])
+    if per_tag is None:
+        per_tag = {}
+        _CAT_CACHE.put(params[0], per_tag)
+    hit = per_tag.get(tag)
+    if hit is None or hit[0] != key or any(r() is not p for r, p in zip(hit[2], params)):
         w = torch.cat([p.detach() for p in params], dim=0)
-        hit = (key, ops.SplitWeight(w), w)
-        _CAT_CACHE[(tag, id(params[0]))] = hit
+        hit = (key, ops.SplitWeight(w), tuple(weakref.ref(p) for p in params))
+        per_tag[tag] = hit
     return hit[1]
 
 
@@ -212,22 +225,23 @@ class AdaptiveGraphPooling(nn.Module):
         return s
 
     @torch.no_grad()
-    def pool(self, x, csr, act=None, part=None):
+    def pool(self, x, csr, act=None, part=None, with_eid=False):
         """Returns (pooled_x [k,C] with `act` applied, pooled CSR, perm int32 [k], node_map int32 [N], scores, pooled Part).
-        Partitioned: scores are all-gathered, every rank runs the same exact top-k, and a selected node stays on its owner."""
+        Partitioned: scores are all-gathered, every rank runs the same exact top-k, and a selected node stays on its owner.
+        with_eid: the pooled CSR keeps the level-0 edge ids (edge_attr[edge_mask] of :327 without the copy)."""
         s = self.scores(x)
         if part is None:
             k = max(1, int(self.ratio * x.size(0)))
             perm, node_map = ops.topk_select(s, k)
             px = ops.pool_gather(x, s, perm, act=act)
-            return px, ops.csr_pool(csr, perm, node_map), perm, node_map, s, None
+            return px, ops.csr_pool(csr, perm, node_map, with_eid), perm, node_map, s, None
         s_full = part.gather(s)
         k = max(1, int(self.ratio * part.n))
         perm, node_map = ops.topk_select(s_full, k)
         new_part = part.pooled(node_map)
         local_perm = (perm[new_part.a:new_part.b] - part.a).contiguous()
         px = ops.pool_gather(x, s, local_perm, act=act)
-        return px, ops.csr_pool(csr, perm, node_map), perm, node_map, s_full, new_part
+        return px, ops.csr_pool(csr, perm, node_map, with_eid), perm, node_map, s_full, new_part
 
     @torch.no_grad()
     def forward(self, x, edge_index, edge_attr=None, batch=None):
@@ -278,21 +292,37 @@ class GraphUNet(nn.Module):
         """part (parallel.Part): x holds the owned rows of a node-partitioned graph; every level keeps its own Part."""
         _require_cuda(x)
         ctx = _ctx_for(x, edge_index, ctx)
-        if edge_attr is not None:
-            raise NotImplementedError("GraphUNet with edge attributes: pooled edge_attr aggregation is not implemented yet; "
-                                      "pass edge_attr=None (the BASELINE configurations do)")
+        # edge attributes (:404-453 thread edge_attr through every level, pooled by `edge_attr[edge_mask]` :327): identity (i)
+        # turns the per-edge term into one [N_l, 32] aggregate per level; the pooled CSRs keep the level-0 edge ids, so the
+        # aggregate of level l reads the ORIGINAL edge_attr and nothing is compacted. No edges / no attributes -> no term
+        # (edge_lin has no bias, P5 substitutes zeros).
+        ea = _edge_attr_or_none(edge_attr, 32)
+        csr0 = ctx.csr if isinstance(ctx, GraphContext) else ctx
+
+        def agg_of(csr, lvl_part, n_lvl):
+            """[rows owned at this level that exist in `csr`, 32] aggregate (D8: the decoder's CSR has fewer rows than nodes)."""
+            if ea is None:
+                return None
+            g = _level0_agg(ctx, ea) if csr is csr0 else ops.edge_attr_aggregate(csr, ea)
+            if lvl_part is None:
+                return g
+            return g[min(lvl_part.a, csr.N):min(lvl_part.b, csr.N)]
+
         a = self.act_name
-        csrs, xs, maps, perms, parts = [ctx.csr], [], [], [], [part]
-        x = self.down_convs[0](x, ctx=csrs[0], part=parts[0])
+        csrs, xs, maps, perms, parts = [csr0], [], [], [], [part]
+        aggs = [agg_of(csr0, part, csr0.N)]
+        x = self.down_convs[0](x, ctx=csrs[0], agg_attr=aggs[0], part=parts[0])
         xs.append(x)
         # `cur` is act(x) of the reference (:419/:432) — for level 0 applied by a tiny un-pool kernel with an empty map
         cur = ops.unpool_add_act(x, x, _neg_map(x), act=a)
         for i in range(self.depth):
-            x = self.down_convs[i + 1](cur, ctx=csrs[-1], part=parts[-1])
+            x = self.down_convs[i + 1](cur, ctx=csrs[-1], agg_attr=aggs[-1], part=parts[-1])
             xs.append(x)
-            cur, pcsr, perm, node_map, _, ppart = self.pools[i].pool(x, csrs[-1], act=a, part=parts[-1])     # pooled + activated
+            cur, pcsr, perm, node_map, _, ppart = self.pools[i].pool(x, csrs[-1], act=a, part=parts[-1],
+                                                                     with_eid=ea is not None)                # pooled + activated
             csrs.append(pcsr); maps.append(node_map); perms.append(perm); parts.append(ppart)
-        x = self.bottom_conv(cur, ctx=csrs[-1], part=parts[-1])
+            aggs.append(agg_of(pcsr, ppart, pcsr.N))
+        x = self.bottom_conv(cur, ctx=csrs[-1], agg_attr=aggs[-1], part=parts[-1])
         for i in range(self.depth):
             j = self.depth - 1 - i
             nm = maps[j]
@@ -300,9 +330,31 @@ class GraphUNet(nn.Module):
                 nm = parts[j].local(nm)
                 nm = torch.where(nm >= 0, nm - parts[j + 1].a, nm).contiguous()
             cur = ops.unpool_add_act(xs[j + 1], x, nm, act=a)
-            x = self.up_convs[i](cur, ctx=csrs[j + 1], n_rows=cur.size(0), part=parts[j])             # D8
+            # D8: level-(j+1) edges and attributes on the level-j node set; rows beyond the pooled CSR have no in-edges
+            agg_j = agg_of(csrs[j + 1], parts[j], csrs[j + 1].N) if part is not None else aggs[j + 1]
+            x = self.up_convs[i](cur, ctx=csrs[j + 1], agg_attr=agg_j, n_rows=cur.size(0), part=parts[j])
         out = ops.linear(x, split_weight(self.final_conv.weight), self.final_conv.bias.detach())
         return (out, perms) if return_perms else out
+
+
+def _edge_attr_or_none(edge_attr, width):
+    """fp32, zero-padded to `width` columns (P7); None when there are no attributes or no edges."""
+    if edge_attr is None or edge_attr.size(0) == 0:
+        return None
+    return _pad_cols(edge_attr.float(), width)
+
+
+def _level0_agg(ctx, ea):
+    """sum_e norm_e * edge_attr_e per destination of the input graph, shared by the encoder and the U-Net (cached on the
+    GraphContext, keyed on the attribute tensor)."""
+    if not isinstance(ctx, GraphContext):
+        return ops.edge_attr_aggregate(ctx, ea)
+    key = (ea.data_ptr(), ea._version, tuple(ea.shape))
+    hit = ctx.agg_attr
+    if hit is None or hit[0] != key:
+        hit = (key, ops.edge_attr_aggregate(ctx.csr, ea), ea)      # `ea` kept alive: the key holds its address
+        ctx.agg_attr = hit
+    return hit[1]
 
 
 _NEG_MAPS = {}
@@ -350,53 +402,72 @@ class MultiHeadAttention(nn.Module):
         lin = [self.k_proj, self.v_proj]
         return split_weight_cat([l.weight for l in lin], "kv"), _qkv_bias(lin)
 
+    def _project(self, query, key, value):
+        """q / k / v projections as views of fused GEMM outputs. Returns (q [B*Lq, D], k [B*Lk, D], v [B*Lk, D], qkv | None,
+        kv_qkv | None) — the last two are the [*, 3D] q|k|v-layout buffers the flash kernels read (kv_qkv None = self-attention)."""
+        D = self.embed_dim
+        q2 = query.reshape(-1, D).contiguous()
+        if key is None or key is query:
+            w, bias = self.qkv_weight()
+            qkv = ops.linear(q2, w, bias)
+            return qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], qkv, None
+        k2 = key.reshape(-1, D).contiguous()
+        bq = self.q_proj.bias.detach() if self.q_proj.bias is not None else None
+        qkv = torch.empty(q2.size(0), 3 * D, dtype=torch.float32, device=q2.device)      # only the q third is written / read
+        ops.linear(q2, split_weight(self.q_proj.weight), bq, out=qkv[:, :D])
+        kv = torch.empty(k2.size(0), 3 * D, dtype=torch.float32, device=q2.device)
+        if value is None or value is key:
+            w, bias = self.kv_weight()
+            ops.linear(k2, w, bias, out=kv[:, D:])
+        else:
+            v2 = value.reshape(-1, D).contiguous()
+            if v2.size(0) != k2.size(0):
+                raise ops.KernelError(f"key has {k2.size(0)} rows but value has {v2.size(0)}")
+            ops.linear(k2, split_weight(self.k_proj.weight), self.k_proj.bias.detach() if self.k_proj.bias is not None else None,
+                       out=kv[:, D:2 * D])
+            ops.linear(v2, split_weight(self.v_proj.weight), self.v_proj.bias.detach() if self.v_proj.bias is not None else None,
+                       out=kv[:, 2 * D:])
+        return qkv[:, :D], kv[:, D:2 * D], kv[:, 2 * D:], qkv, kv
+
     @torch.no_grad()
     def forward(self, query, key=None, value=None, key_padding_mask=None, need_weights=True, attn_mask=None,
                 average_attn_weights=True):
+        """core/attention.py:73-181 (eval: both dropouts are identities). Without weights and masks the core is the flash
+        kernel (all batch elements in one launch, one segment each); weights or masks go through the dense kernel
+        (dgdm_mha_dense), whose output is O(L_q L_k) anyway."""
         _require_cuda(query)
-        if key_padding_mask is not None or (attn_mask is not None):
-            raise NotImplementedError("explicit attn_mask / key_padding_mask: use SpatialAttention for the distance bias; "
-                                      "arbitrary masks are not implemented")
         if not self.batch_first:
             query = query.transpose(0, 1)
             key = key.transpose(0, 1) if key is not None else None
             value = value.transpose(0, 1) if value is not None else None
-        if value is not None and value is not key and not (key is None):
-            if value.data_ptr() != key.data_ptr():
-                raise NotImplementedError("distinct key and value tensors are not implemented")
         B, L, D = query.shape
-        outs, ws = [], []
-        for b in range(B):
-            q_in = query[b].contiguous()
-            if key is None or key.data_ptr() == query.data_ptr():
-                w, bias = self.qkv_weight()
-                qkv = ops.linear(q_in, w, bias)
-                kv_qkv, Lk = qkv, L
-            else:
-                k_in = key[b].contiguous()
-                Lk = k_in.size(0)
-                w, bias = self.qkv_weight()
-                qkv = ops.linear(q_in, w, bias)             # only the q third is used
-                kv_qkv = ops.linear(k_in, w, bias)
-            dev = query.device
-            qseg = torch.tensor([0, L], dtype=torch.int32, device=dev)
-            kseg = torch.tensor([0, Lk], dtype=torch.int32, device=dev)
-            if self.head_dim not in (4, 8, 16, 32, 64):
-                raise NotImplementedError(f"head_dim {self.head_dim}: supported head widths are 4, 8, 16, 32, 64")
-            o = ops.spatial_attention_any(qkv, None, qseg, 1, self.num_heads, kv_qkv=kv_qkv if kv_qkv is not qkv else None, kseg_ptr=kseg)
-            o = ops.linear(o, split_weight(self.out_proj.weight), self.out_proj.bias.detach() if self.out_proj.bias is not None else None)
-            outs.append(o)
-            if need_weights:
-                if Lk != L:
-                    raise NotImplementedError("need_weights with cross attention is not implemented")
-                w_avg = ops.spatial_attention_weights(qkv, None, self.num_heads)
-                if not average_attn_weights:
-                    raise NotImplementedError("average_attn_weights=False is not implemented")
-                ws.append(w_avg)
-        out = torch.stack(outs, 0)
+        o, w = self._core(query, key, value, key_padding_mask, need_weights, attn_mask, average_attn_weights)
+        out = ops.linear(o, split_weight(self.out_proj.weight), self.out_proj.bias.detach() if self.out_proj.bias is not None else None)
+        out = out.view(B, L, D)
         if not self.batch_first:
             out = out.transpose(0, 1)
-        return out, (torch.stack(ws, 0) if need_weights else None)
+        return out, w
+
+    def _core(self, query, key, value, key_padding_mask, need_weights, attn_mask, average_attn_weights, *, _pos=None,
+              _pos_by_head=False, _temperature=1.0):
+        """Projections + softmax(QK^T/sqrt(hd) + masks) V on batch-first inputs; returns (o [B*L, D] before out_proj, weights).
+        `_pos*`: SpatialAttention's distance bias, formed inside the kernel instead of as a [B, L, L] tensor."""
+        B, L, D = query.shape
+        Lk = L if key is None else key.size(1)
+        q, k, v, qkv, kv = self._project(query, key, value)
+        dense = need_weights or attn_mask is not None or key_padding_mask is not None or _pos is not None \
+            or self.head_dim not in (4, 8, 16, 32, 64)
+        w = None
+        if dense:
+            o, w = ops.mha_dense(q, k, v, B, L, Lk, self.num_heads, attn_mask=attn_mask, key_padding_mask=key_padding_mask,
+                                 pos_q=_pos, pos_k=_pos, pos_by_head=_pos_by_head, temperature=_temperature,
+                                 need_weights=need_weights, per_head=not average_attn_weights)
+        else:
+            dev = query.device
+            qseg = torch.arange(0, (B + 1) * L, L, dtype=torch.int32, device=dev)
+            kseg = torch.arange(0, (B + 1) * Lk, Lk, dtype=torch.int32, device=dev)
+            o = ops.spatial_attention_any(qkv, None, qseg, B, self.num_heads, kv_qkv=kv, kseg_ptr=kseg, max_seg=Lk)
+        return o, w
 
 
 def _qkv_bias(linears):
@@ -460,15 +531,23 @@ class SpatialAttention(nn.Module):
 
     @torch.no_grad()
     def forward(self, x, positions, mask=None):
-        """Reference signature: x [B,n,D], positions [B,n,2] -> (out [B,n,D], weights [B,n,n])."""
+        """Reference signature (core/attention.py:285-327): x [B,n,D], positions [B,n,2] -> (out [B,n,D], weights [B,n,n]).
+        The PE min/max is taken over the WHOLE positions tensor (:233-236), not per batch element. The bias is added as
+        `[B,H,n,n] += bias[B,n,n]`, which torch only broadcasts for B == 1 — or, by accident, B == H, where element h of the
+        bias lands on HEAD h of every batch element; both behaviours are reproduced, any other B raises like the reference."""
         _require_cuda(x)
-        if mask is not None:
-            raise NotImplementedError("additional attention mask is not implemented")
         B, n, D = x.shape
-        seg_host = [i * n for i in range(B + 1)]
-        seg_ptr = torch.tensor(seg_host, dtype=torch.int32, device=x.device)
-        out, ws = self.forward_nodes(x.reshape(B * n, D).contiguous(), positions.reshape(B * n, 2), seg_ptr, B, seg_host, True)
-        return out.view(B, n, D), torch.stack(ws, 0)
+        if B != 1 and B != self.num_heads:
+            raise RuntimeError(f"The size of tensor a ({self.num_heads}) must match the size of tensor b ({B}) at non-singleton dimension 1")
+        x2 = x.reshape(B * n, D).contiguous()
+        pos = positions.reshape(B * n, 2).float().contiguous()
+        one = torch.tensor([0, B * n], dtype=torch.int32, device=x.device)
+        xp = ops.spatial_pe_add(x2, pos, one, 1)                                    # global min / max: a single segment
+        att = self.attention
+        o, w = att._core(xp.view(B, n, D), None, None, None, True, mask, True, _pos=pos.view(B, n, 2), _pos_by_head=B != 1,
+                         _temperature=self.temperature)
+        out = ops.linear(o, split_weight(att.out_proj.weight), att.out_proj.bias.detach(), r_pre=x2, ln1=_ln(self.norm))
+        return out.view(B, n, D), w
 
 
 # ------------------------------------------------------------------------------------------ diffusion
@@ -765,8 +844,9 @@ class GraphEncoder(nn.Module):
         _require_cuda(x)
         ctx = _ctx_for(x, edge_index, ctx)
         agg = None
-        if edge_attr is not None and self.use_edge_features:
-            agg = ops.edge_attr_aggregate(ctx.csr, _pad_cols(edge_attr.float(), 32))
+        ea = _edge_attr_or_none(edge_attr, 32) if self.use_edge_features else None
+        if ea is not None:
+            agg = _level0_agg(ctx, ea)
             if part is not None:
                 agg = part.local(agg)
         h, outs = x, []

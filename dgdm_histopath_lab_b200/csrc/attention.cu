@@ -643,11 +643,11 @@ extern "C" int dgdm_spatial_attention(const float* q_qkv, int ld_q, const float*
 #define ATT_LAUNCH(PREC, FULLV)                                                                                          \
   do {                                                                                                                   \
     constexpr int smem = 2 * ((PREC ? 4 : 2) * ATT_KS * ATT_ROWB + ATT_KS * 8);                                          \
-    static bool set = false;                                                                                             \
-    if (!set) {                                                                                                          \
+    static PerDeviceOnce set;                                                                                            \
+    if (set.needed()) {                                                                                                  \
       if (cudaFuncSetAttribute(spatial_attn_kernel<16, PREC, FULLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)  \
           != cudaSuccess) return DGDM_ERR_LAUNCH;                                                                        \
-      set = true;                                                                                                        \
+      set.mark();                                                                                                        \
     }                                                                                                                    \
     spatial_attn_kernel<16, PREC, FULLV><<<grid, ATT_THREADS, smem, s>>>(p);                                             \
   } while (0)

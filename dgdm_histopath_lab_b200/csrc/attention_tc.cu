@@ -520,10 +520,10 @@ int attn_tc_launch(const float* q_qkv, int ld_q, const float* q_pos, const int* 
   const float pscale = LOG2E / temperature;
   attn_tc_blkptr_kernel<<<1, 32, 0, s>>>(kseg_ptr, num_seg, blk_ptr);
   attn_tc_prep_kernel<<<(unsigned)nblk_max, 256, 0, s>>>(kv_qkv, ld_kv, kv_pos, kseg_ptr, blk_ptr, num_seg, pscale, img);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.needed()) {
     if (cudaFuncSetAttribute(spatial_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM) != cudaSuccess) return DGDM_ERR_LAUNCH;
-    attr_set = true;
+    attr_set.mark();
   }
   AttnTcParams p;
   p.q_qkv = q_qkv; p.ld_q = ld_q; p.q_pos = q_pos; p.qseg = qseg_ptr; p.kseg = kseg_ptr; p.num_seg = num_seg; p.Nq = Nq; p.nsplit = ns;

@@ -390,13 +390,13 @@ static int launch_topk(const double* D2, int n, int nq, int k, int* idx, double*
     row_topk_kernel<K><<<blocks, 128, sm, s>>>(D2, n, nq, k, idx, dist);
   } else if (k <= 32) {
     constexpr int K = 32; const size_t sm = (size_t)4 * 32 * K * 12;
-    static bool set = false;
-    if (!set) { if (cudaFuncSetAttribute(row_topk_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return DGDM_ERR_LAUNCH; set = true; }
+    static PerDeviceOnce set;
+    if (set.needed()) { if (cudaFuncSetAttribute(row_topk_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return DGDM_ERR_LAUNCH; set.mark(); }
     row_topk_kernel<K><<<blocks, 128, sm, s>>>(D2, n, nq, k, idx, dist);
   } else {
     constexpr int K = KNN_MAXK; const size_t sm = (size_t)4 * 32 * K * 12;
-    static bool set = false;
-    if (!set) { if (cudaFuncSetAttribute(row_topk_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return DGDM_ERR_LAUNCH; set = true; }
+    static PerDeviceOnce set;
+    if (set.needed()) { if (cudaFuncSetAttribute(row_topk_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return DGDM_ERR_LAUNCH; set.mark(); }
     row_topk_kernel<K><<<blocks, 128, sm, s>>>(D2, n, nq, k, idx, dist);
   }
   return DGDM_OK;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <atomic>
 #include "../../include/dgdm_b200.h"
 
 #define DGDM_CHECK_LAUNCH() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return DGDM_ERR_LAUNCH; } while (0)
@@ -10,6 +11,14 @@
 namespace dgdm {
 
 constexpr int kWarp = 32;
+
+// cudaFuncSetAttribute is per device / context: remember which devices of this process have been configured (bit per ordinal).
+// Racing callers at worst repeat the (idempotent) attribute call.
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done{0ull};
+  bool needed() const { int d = 0; cudaGetDevice(&d); return !((done.load(std::memory_order_acquire) >> (d & 63)) & 1ull); }
+  void mark() { int d = 0; cudaGetDevice(&d); done.fetch_or(1ull << (d & 63), std::memory_order_release); }
+};
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

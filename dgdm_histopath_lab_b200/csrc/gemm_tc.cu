@@ -494,15 +494,15 @@ __global__ void split_weight_kernel(const float* __restrict__ W, int N, int K, u
 static int g_num_sms = 0;
 
 static int launch_gemm(const dgdm_gemm_params& p, long long plane_stride, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.needed()) {
     if (cudaFuncSetAttribute(gemm_f16x2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(gemm_f16x2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM) != cudaSuccess)
       return DGDM_ERR_LAUNCH;
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_num_sms <= 0) g_num_sms = 148;
-    attr_set = true;
+    attr_set.mark();
   }
   GemmSched sc;
   const int ch_rows = p.N < GEMM_NCHUNK ? p.N : GEMM_NCHUNK;

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256) spmm_gcn_kernel(const int* __restrict__ r
       const float4 hs = ldg4(H + (size_t)(h_row0 + row) * ldh + idx);  // self loop last (add_self_loops appends)
       float4 a = acc[v];
       a.x = fmaf(selfw, hs.x, a.x); a.y = fmaf(selfw, hs.y, a.y); a.z = fmaf(selfw, hs.z, a.z); a.w = fmaf(selfw, hs.w, a.w);
-      if (addend) { const float4 t = ldg4(addend + (size_t)row * ld_add + idx); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+      if (addend && row < n_csr_rows) { const float4 t = ldg4(addend + (size_t)row * ld_add + idx); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
       if (bias) { const float4 t = ldg4(bias + idx); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
       apply_act4(a, act);
       *reinterpret_cast<float4*>(out + (size_t)row * ldo + idx) = a;
@@ -352,7 +352,8 @@ __global__ void __launch_bounds__(256) csr_pool_count_kernel(const int* __restri
 __global__ void __launch_bounds__(256) csr_pool_fill_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
                                                             const int* __restrict__ perm, const int* __restrict__ node_map, int k,
                                                             const int* __restrict__ p_rowptr, const float* __restrict__ p_dinv,
-                                                            int* __restrict__ p_col, float* __restrict__ p_norm) {
+                                                            int* __restrict__ p_col, float* __restrict__ p_norm,
+                                                            const int* __restrict__ eid, int* __restrict__ p_eid) {
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= k) return;
   const int old = perm[r];
@@ -368,6 +369,7 @@ __global__ void __launch_bounds__(256) csr_pool_fill_kernel(const int* __restric
       const int pos = outp + __popc(b & ((1u << lane) - 1u));
       p_col[pos] = nm;
       p_norm[pos] = p_dinv[nm] * dr;
+      if (p_eid) p_eid[pos] = eid[e];         // level-0 edge id: edge_attr[edge_mask] (core/graph_layers.py:327) without a copy
     }
     outp += __popc(b);
   }
@@ -501,14 +503,15 @@ extern "C" int dgdm_pool_gather(const float* X, int ldx, int C, const float* sco
   return DGDM_OK;
 }
 
-extern "C" int dgdm_csr_pool(const int* rowptr, const int* col, int N, const int* perm, const int* node_map, int k,
-                             int* p_rowptr, int* p_col, float* p_norm, float* p_dinv, int* work, void* stream) {
+extern "C" int dgdm_csr_pool(const int* rowptr, const int* col, const int* eid, int N, const int* perm, const int* node_map, int k,
+                             int* p_rowptr, int* p_col, int* p_eid, float* p_norm, float* p_dinv, int* work, void* stream) {
   if (!rowptr || !perm || !node_map || !p_rowptr || !p_dinv || !work || k <= 0 || k > N) return DGDM_ERR_INVALID;
+  if (p_eid && !eid) return DGDM_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
   int* cnt = work;
   csr_pool_count_kernel<<<(k + 7) / 8, 256, 0, s>>>(rowptr, col, perm, node_map, k, cnt, p_dinv);
   launch_exclusive_scan(cnt, p_rowptr, k, work + k + 8, (k / SCAN_TILE + 2) * 2 + 8, s);
-  csr_pool_fill_kernel<<<(k + 7) / 8, 256, 0, s>>>(rowptr, col, perm, node_map, k, p_rowptr, p_dinv, p_col, p_norm);
+  csr_pool_fill_kernel<<<(k + 7) / 8, 256, 0, s>>>(rowptr, col, perm, node_map, k, p_rowptr, p_dinv, p_col, p_norm, eid, p_eid);
   DGDM_CHECK_LAUNCH();
   return DGDM_OK;
 }

@@ -154,6 +154,7 @@ class GlobalAttentionPool(nn.Module):
 
 class DGDMModel(nn.Module):
     """Dynamic Graph Diffusion Model — same public API as the reference class (models/dgdm_model.py:45-61,271-277,447,527)."""
+    _warned_no_grad = False
 
     def __init__(self, node_features=768, hidden_dims=[512, 256, 128], num_diffusion_steps=10, attention_heads=8, dropout=0.1,
                  graph_layers=4, use_spatial_attention=True, use_hierarchical=True, diffusion_schedule="cosine",
@@ -316,6 +317,11 @@ class DGDMModel(nn.Module):
                 self._validate_forward_inputs(data, mode, return_attention, return_embeddings)
         except Exception as e:
             raise ModelInferenceError(f"Input validation failed: {e}")
+        if (self.training or torch.is_grad_enabled()) and mode in ("pretrain", "finetune") and not DGDMModel._warned_no_grad:
+            # the backward kernels are SURVEY §8(f) rank 1: say so instead of silently returning graph-less losses
+            DGDMModel._warned_no_grad = True
+            warnings.warn("dgdm_histopath_lab_b200 computes the forward only: outputs carry no autograd graph and dropout is "
+                          "the identity (eval semantics) even in train() mode; loss.backward() will not reach the parameters")
         try:
             with torch.no_grad():
                 return self._forward_impl(data, mode, return_attention, return_embeddings, rng)

@@ -259,7 +259,8 @@ def pool_gather(x, scores, perm, act=None):
     return out
 
 
-def csr_pool(csr, perm, node_map):
+def csr_pool(csr, perm, node_map, with_eid=False):
+    """with_eid: the pooled CSR carries the level-0 edge ids (for edge_attr aggregation on pooled levels)."""
     lib = _lib.load()
     k = perm.numel()
     dev = perm.device
@@ -268,9 +269,11 @@ def csr_pool(csr, perm, node_map):
     p_norm = torch.empty(max(csr.E, 1), dtype=torch.float32, device=dev)
     p_dinv = torch.empty(k, dtype=torch.float32, device=dev)
     work = torch.empty(k + 2 * (k // 2048 + 2) + 64, dtype=torch.int32, device=dev)      # counts + scan scratch
-    _check(lib.dgdm_csr_pool(_p(csr.rowptr), _p(csr.col), csr.N, _p(perm), _p(node_map), k, _p(p_rowptr), _p(p_col),
-                             _p(p_norm), _p(p_dinv), _p(work), _stream()), "dgdm_csr_pool")
-    return CSR(p_rowptr, p_col, None, p_norm, p_dinv, k, csr.E)   # E is an upper bound; the true count is rowptr[k]
+    with_eid = with_eid and csr.eid is not None
+    p_eid = torch.empty(max(csr.E, 1), dtype=torch.int32, device=dev) if with_eid else None
+    _check(lib.dgdm_csr_pool(_p(csr.rowptr), _p(csr.col), _p(csr.eid) if with_eid else None, csr.N, _p(perm), _p(node_map), k,
+                             _p(p_rowptr), _p(p_col), _p(p_eid), _p(p_norm), _p(p_dinv), _p(work), _stream()), "dgdm_csr_pool")
+    return CSR(p_rowptr, p_col, p_eid, p_norm, p_dinv, k, csr.E)   # E is an upper bound; the true count is rowptr[k]
 
 
 def unpool_add_act(skip, x, node_map, act=None):
@@ -374,6 +377,49 @@ def spatial_attention_weights(qkv, pos, heads, temperature=1.0):
     _check(lib.dgdm_spatial_attention_weights(_p(_f32c(qkv)), qkv.stride(0), _p(pos), n, D3 // 3, heads, float(temperature),
                                               _p(w), _stream()), "dgdm_spatial_attention_weights")
     return w
+
+
+def mha_dense(q, k, v, B, Lq, Lk, heads, *, attn_mask=None, key_padding_mask=None, pos_q=None, pos_k=None, pos_by_head=False,
+              temperature=1.0, need_weights=True, per_head=False):
+    """Dense MultiHeadAttention core on projected rows q [B*Lq, D], k / v [B*Lk, D] (row stride may exceed D).
+    attn_mask: float (additive) or bool (True = -inf), any shape broadcastable to [B, H, Lq, Lk] by torch's rules.
+    Returns (out [B*Lq, D], weights [B*H, Lq, Lk] | [B, Lq, Lk] | None)."""
+    lib = _lib.load()
+    D = q.size(1)
+    dev = q.device
+    fmask = bmask = None
+    strides = (0, 0, 0, 0)
+    if attn_mask is not None:
+        m = attn_mask
+        if m.dim() > 4:
+            raise KernelError(f"attn_mask with {m.dim()} dims")
+        m4 = m.reshape((1,) * (4 - m.dim()) + tuple(m.shape))
+        for have, want in zip(m4.shape, (B, heads, Lq, Lk)):
+            if have not in (1, want):           # same failure torch's `attn_scores += attn_mask` raises
+                raise RuntimeError(f"The size of tensor a ({(B, heads, Lq, Lk)}) must match the size of tensor b ({tuple(m.shape)}) "
+                                   "at a non-singleton dimension")
+        strides = tuple(0 if m4.size(i) == 1 else m4.stride(i) for i in range(4))
+        if m.dtype == torch.bool:
+            bmask = m4
+        else:
+            fmask = m4 = m4.float()
+            strides = tuple(0 if m4.size(i) == 1 else m4.stride(i) for i in range(4))
+    kpm = None
+    if key_padding_mask is not None:
+        kpm = key_padding_mask.to(torch.bool).contiguous()
+        assert kpm.shape == (B, Lk), (kpm.shape, B, Lk)
+    out = torch.empty(B * Lq, D, dtype=torch.float32, device=dev)
+    w = None
+    if need_weights:
+        w = torch.empty((B * heads, Lq, Lk) if per_head else (B, Lq, Lk), dtype=torch.float32, device=dev)
+    pq = None if pos_q is None else _f32c(pos_q.float().contiguous())
+    pk = None if pos_k is None else _f32c(pos_k.float().contiguous())
+    _check(lib.dgdm_mha_dense(_p(_f32c(q)), q.stride(0), _p(_f32c(k)), k.stride(0), _p(_f32c(v)), v.stride(0), B, Lq, Lk, D, heads,
+                              _p(fmask), _p(bmask.view(torch.uint8)) if bmask is not None else None, strides[0], strides[1],
+                              strides[2], strides[3], _p(kpm.view(torch.uint8)) if kpm is not None else None, _p(pq), _p(pk),
+                              int(bool(pos_by_head)), float(temperature), _p(out), out.stride(0), _p(w), int(bool(per_head)),
+                              _stream()), "dgdm_mha_dense")
+    return out, w
 
 
 def attention_pool(q_tok, kv, seg_ptr, num_seg, heads):

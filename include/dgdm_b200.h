@@ -97,7 +97,8 @@ int dgdm_csr_build(const int64_t* edge_index, int E, int N, int* rowptr, int* co
 
 /* GraphConvolution.propagate + bias + activation (core/graph_layers.py:92-110, 233-239) for output rows i in [0, n_rows):
  *   out[i,:] = act( sum_{e in row i, edge order} norm[e]*H[col[e],:] + dinv[i]^2*H[h_row0+i,:] (+addend[i,:]) (+bias) )
- * Rows i >= n_csr_rows (decoder levels of GraphUNet, D8) have only the self loop with weight 1.
+ * Rows i >= n_csr_rows (decoder levels of GraphUNet, D8) have only the self loop with weight 1 and no addend
+ * (addend holds n_csr_rows rows).
  * Node-partitioned graphs: a rank that owns rows [a,b) passes rowptr+a, dinv+a, h_row0 = a and the all-gathered H
  * (col holds global indices); single GPU: h_row0 = 0.
  * C % 4 == 0, C <= 1024. Deterministic: fixed in-row order, self loop last, no atomics. */
@@ -119,8 +120,11 @@ size_t dgdm_topk_pool_work_ints(int N);
 int dgdm_topk_select(const float* scores, int N, int k, int* perm, int* node_map, int* work, void* stream);
 int dgdm_pool_gather(const float* X, int ldx, int C, const float* scores, const int* perm, int k, int act,
                      float* out, int ldo, void* stream);
-int dgdm_csr_pool(const int* rowptr, const int* col, int N, const int* perm, const int* node_map, int k,
-                  int* p_rowptr, int* p_col, float* p_norm, float* p_dinv, int* work, void* stream);
+/* eid / p_eid (both NULL, or both given): the pooled entries keep the LEVEL-0 edge id of the edge they came from, so that
+ * `edge_attr[edge_mask]` (:327) never has to be materialised — dgdm_edge_attr_aggregate on the pooled CSR indexes the
+ * original edge_attr. */
+int dgdm_csr_pool(const int* rowptr, const int* col, const int* eid, int N, const int* perm, const int* node_map, int k,
+                  int* p_rowptr, int* p_col, int* p_eid, float* p_norm, float* p_dinv, int* work, void* stream);
 /* GraphUNet un-pool + skip + act (core/graph_layers.py:441-452): out[i] = act(skip[i] + (node_map[i]>=0 ? x[node_map[i]] : 0)) */
 int dgdm_unpool_add_act(const float* skip, int ld_skip, const float* x, int ldx, const int* node_map, int N,
                         int C, int act, float* out, int ldo, void* stream);
@@ -159,6 +163,21 @@ int dgdm_spatial_attention(const float* q_qkv, int ld_q, const float* q_pos, con
 /* Head-averaged attention weights [n,n] of ONE graph segment (return_attention=True; O(n^2) output). */
 int dgdm_spatial_attention_weights(const float* qkv, int ld, const float* pos, int n, int D, int heads,
                                    float temperature, float* weights /*[n,n]*/, void* stream);
+
+/* MultiHeadAttention.forward core (core/attention.py:113-172) for the options the flash kernels do not take: additive
+ * (`attn_scores += attn_mask`, :142) or boolean (`masked_fill_(-inf)`, :140) masks with torch-broadcast strides in ELEMENTS over
+ * (batch, head, query, key) — stride 0 = broadcast —, key_padding_mask [B,Lk] (:145-150), cross attention (Lq != Lk), a value
+ * tensor distinct from the key, and weights per head [B*H,Lq,Lk] (average_attn_weights=False, :172) or head-averaged
+ * [B,Lq,Lk] (:170). q [B*Lq, D], k / v [B*Lk, D] are the PROJECTED rows. Optional spatial bias -|p_i - p_j| / temperature
+ * (SpatialAttention.compute_spatial_bias, :261-283) from pos_q [P,Lq,2] / pos_k [P,Lk,2]; pos_by_head = 1 indexes P by the
+ * head instead of the batch element: that is what the reference's `[B,H,L,L] += bias[B,L,L]` broadcast does when B == H > 1
+ * (a quirk reproduced as is; for other B > 1 the reference raises). A fully masked row yields NaN like torch's softmax.
+ * Exact fp32 on CUDA cores, O(Lq*Lk*D) — the public-API path, not the model's forward. */
+int dgdm_mha_dense(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int B, int Lq, int Lk,
+                   int D, int heads, const float* mask, const unsigned char* bool_mask, long long ms_b, long long ms_h,
+                   long long ms_q, long long ms_k, const unsigned char* key_padding_mask, const float* pos_q,
+                   const float* pos_k, int pos_by_head, float temperature, float* out, int ldo, float* weights,
+                   int per_head, void* stream);
 
 /* GlobalAttentionPool (models/dgdm_model.py:588-615): one query (q_tok = q_proj(global_token), [D]) per graph
  * over that graph's keys/values kv [N, 2*D] (k|v). out [num_seg, D] before out_proj.

@@ -164,8 +164,11 @@ def graph_encoder(sd, p, x, edge_index, edge_attr, num_layers, act="gelu", retur
 
 
 # ----------------------------------------------------------------------------- attention
-def multi_head_attention(sd, p, query, key=None, value=None, num_heads=8, attn_mask=None, need_weights=True):
-    """MultiHeadAttention.forward, core/attention.py:73-181 (batch_first, eval). Inputs [B, L, D]."""
+def multi_head_attention(sd, p, query, key=None, value=None, num_heads=8, attn_mask=None, need_weights=True,
+                         key_padding_mask=None, average_attn_weights=True):
+    """MultiHeadAttention.forward, core/attention.py:73-181 (batch_first, eval). Inputs [B, L, D]. Masks follow the reference
+    literally: bool attn_mask -> masked_fill(-inf) (:140), float -> `scores += mask` with torch broadcasting (:142),
+    key_padding_mask [B, Lk] -> -inf (:145-150); weights head-averaged (:170) or [B*H, Lq, Lk] (:172)."""
     key = query if key is None else key
     value = key if value is None else value
     b, lq, d = query.shape
@@ -175,25 +178,41 @@ def multi_head_attention(sd, p, query, key=None, value=None, num_heads=8, attn_m
     v = _lin(sd, p + ".v_proj", value).view(b, -1, num_heads, hd).transpose(1, 2)
     s = torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(hd)
     if attn_mask is not None:
-        s = s + attn_mask
+        s = s.masked_fill(attn_mask, float("-inf")) if attn_mask.dtype == torch.bool else s + attn_mask
+    if key_padding_mask is not None:
+        s = s.masked_fill(key_padding_mask.unsqueeze(1).unsqueeze(2), float("-inf"))
     w = F.softmax(s, dim=-1)
     o = torch.matmul(w, v).transpose(1, 2).contiguous().view(b, lq, d)
     o = _lin(sd, p + ".out_proj", o)
-    return o, (w.mean(dim=1) if need_weights else None)
+    if not need_weights:
+        return o, None
+    return o, (w.mean(dim=1) if average_attn_weights else w.reshape(b * num_heads, lq, -1))
 
 
 def spatial_positional_encoding(pos, embed_dim):
-    """SpatialAttention.get_positional_encoding, core/attention.py:225-259. pos [N,2] -> [N, embed_dim]."""
+    """SpatialAttention.get_positional_encoding, core/attention.py:225-259. pos [..., 2] -> [..., embed_dim]; the min / max
+    are taken over the WHOLE tensor (:233-236)."""
     pn = pos.float()
     if pn.numel() > 0:
         pn = (pn - pn.min()) / (pn.max() - pn.min() + 1e-8)
-    pe = torch.zeros(pos.size(0), embed_dim)
+    pe = torch.zeros(tuple(pos.shape[:-1]) + (embed_dim,))
     div = torch.exp(torch.arange(0, embed_dim // 2, 2) * -(math.log(10000.0) / (embed_dim // 2)))
-    pe[:, 0::4] = torch.sin(pn[:, 0:1] * div)
-    pe[:, 1::4] = torch.cos(pn[:, 0:1] * div)
-    pe[:, 2::4] = torch.sin(pn[:, 1:2] * div)
-    pe[:, 3::4] = torch.cos(pn[:, 1:2] * div)
+    pe[..., 0::4] = torch.sin(pn[..., 0:1] * div)
+    pe[..., 1::4] = torch.cos(pn[..., 0:1] * div)
+    pe[..., 2::4] = torch.sin(pn[..., 1:2] * div)
+    pe[..., 3::4] = torch.cos(pn[..., 1:2] * div)
     return pe
+
+
+def spatial_attention_batched(sd, p, x, pos, num_heads=8, temperature=1.0, mask=None):
+    """SpatialAttention.forward with its public signature, core/attention.py:285-327: x [B,n,D], pos [B,n,2]. The bias
+    [B,n,n] is added to scores [B,H,n,n] by plain torch broadcasting — defined only for B == 1 or (accidentally) B == H."""
+    pe = spatial_positional_encoding(pos, x.size(-1))
+    bias = -torch.norm(pos.unsqueeze(2) - pos.unsqueeze(1), dim=-1) / temperature
+    if mask is not None:
+        bias = mask + bias
+    o, w = multi_head_attention(sd, p + ".attention", x + pe, num_heads=num_heads, attn_mask=bias, need_weights=True)
+    return _ln(sd, p + ".norm", x + o), w
 
 
 def spatial_attention(sd, p, x, pos, num_heads=8, temperature=1.0, need_weights=False):
@@ -305,6 +324,25 @@ def classification_head(sd, p, x, act="gelu"):
 
 
 # ----------------------------------------------------------------------------- model
+def apply_entity_masking(x, mask_indices, mask_token):
+    """DGDMModel._apply_entity_masking, models/dgdm_model.py:482-506 with the draws injected (randperm(n)[:k], randn(F))."""
+    out = x.clone()
+    if mask_indices is not None and mask_indices.numel() > 0:
+        node_mask = torch.zeros(x.size(0), dtype=torch.bool)
+        node_mask[mask_indices] = True
+        out[node_mask] = mask_token
+    return out
+
+
+def pretrain_step(sd, cfg, x, edge_index, edge_attr=None, batch=None, pos=None, rng=None):
+    """DGDMModel.pretrain_step, models/dgdm_model.py:447-480: mask, forward(mode='pretrain'); the reconstruction branch is
+    dead (D12) so total_pretrain_loss = diffusion_loss."""
+    xm = apply_entity_masking(x, rng.get("mask_indices"), rng.get("mask_token"))
+    out = dgdm_forward(sd, cfg, xm, edge_index, edge_attr, batch, pos, mode="pretrain", rng=rng)
+    out["total_pretrain_loss"] = out["diffusion_loss"]
+    return out
+
+
 def dgdm_forward(sd, cfg, x, edge_index, edge_attr=None, batch=None, pos=None, mode="inference",
                  rng=None, return_stages=False):
     """DGDMModel.forward + _forward_continue, models/dgdm_model.py:271-403 (eval; P1-P7).

@@ -55,10 +55,133 @@ def pretrain_draws(seed, sizes, dim, steps):
     return t, noise, target
 
 
+BUILDER_MODEL_CFG = dict(node_features=64, hidden_dims=[64, 32, 32], num_diffusion_steps=10, attention_heads=2, graph_layers=3,
+                         num_classes=3)
+
+
+def _builder_600(ns):
+    """The reference's own TissueGraphBuilder.build_graph on 600 synthetic patches (64-d clustered features, jittered grid)."""
+    import logging
+    n = 600
+    feats = synth.clustered_features(n, d=64, num_clusters=12, seed=21, sigma_lo=0.05, sigma_hi=0.11)
+    xs, ys, dims = synth.jittered_grid_coords(n, seed=21, extent=3000)
+    sp = ns["sp"]
+    patches = [sp.PatchInfo(int(xs[i]), int(ys[i]), 0, 20.0, f"s_patch_{i:06d}", 0.9, feats[i]) for i in range(n)]
+    slide = sp.SlideData("s", patches, {"dimensions": dims})
+    tb = ns["TissueGraphBuilder"].__new__(ns["TissueGraphBuilder"])
+    tb.__dict__.update(dict(feature_extractor="none", spatial_k=8, morphological_k=16, edge_threshold=0.7, hierarchical_levels=3,
+                            min_component_size=5, use_adaptive_threshold=True, feature_dim=64))
+    tb.logger = logging.getLogger("golden")
+    return tb.build_graph(slide)
+
+
+def round2(ns):
+    """Round-2 fixtures: edge attributes through the WHOLE model (GraphUNet pooled levels included), the reference's serving
+    pipeline build_graph -> forward (evaluation/predictor.py:188-215), pretrain_step with injected draws, public
+    MultiHeadAttention / SpatialAttention calls (masks, cross attention, per-head weights, B > 1)."""
+    m = ref_model(ns, SMALL_CFG)
+    b = small_batch()
+    g = torch.Generator().manual_seed(5)
+    ea32 = torch.randn(b.edge_index.size(1), 32, generator=g)
+    ea2 = torch.rand(b.edge_index.size(1), 2, generator=g)
+    outs = {}
+    for tag, ea in (("ea32", ea32), ("ea2", ea2)):
+        rb = ns["Batch"](x=b.x, edge_index=b.edge_index, edge_attr=ea, pos=b.pos)
+        rb.batch = b.batch
+        st = {}
+        hk = m.hierarchical_processor.register_forward_hook(lambda mod, i, o: st.__setitem__("unet", o.detach().clone()))
+        with torch.no_grad():
+            o = m(rb, return_embeddings=True)
+        hk.remove()
+        outs[tag + "_node_embeddings"] = o["node_embeddings"].numpy()
+        outs[tag + "_graph_embedding"] = o["graph_embedding"].numpy()
+        outs[tag + "_logits"] = o["classification_logits"].numpy()
+        outs[tag + "_unet"] = st["unet"].numpy()
+    # standalone GraphUNet on a single graph with attributes (perms recorded through the pools)
+    d1 = synth.tile_graph(257, 32, seed=5)
+    ea1 = torch.randn(d1.edge_index.size(1), 32, generator=g)
+    perms = []
+    hks = [pl.register_forward_hook(lambda mod, i, o: perms.append(o[3].clone())) for pl in m.hierarchical_processor.pools]
+    with torch.no_grad():
+        u = m.hierarchical_processor(d1.x, d1.edge_index, ea1)
+    [h.remove() for h in hks]
+    outs["unet1_out"] = u.numpy()
+    for i, pm in enumerate(perms):
+        outs[f"unet1_perm{i}"] = pm.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "edge_attr_model.npz"), **outs)
+    print("edge_attr_model: unet perms", [int(p.numel()) for p in perms])
+
+    # ---- build_graph -> forward: the graph the reference's builder emits (edge_attr [2M,2], pixel-coordinate pos) into its model
+    gph = _builder_600(ns)
+    mb = ref_model(ns, BUILDER_MODEL_CFG, seed=3)
+    with torch.no_grad():
+        ob = mb(gph, return_embeddings=True)
+    # (the empty-edge graph the builder emits when nothing passes the threshold — edge_attr (0,1) — makes the reference's own
+    # validation raise: `edge_index.max()` on an empty tensor, models/dgdm_model.py:676; the product accepts it and is
+    # checked against the oracle instead)
+    np.savez_compressed(os.path.join(GOLDEN, "builder_forward_600.npz"), node_embeddings=ob["node_embeddings"].numpy(),
+                        graph_embedding=ob["graph_embedding"].numpy(), logits=ob["classification_logits"].numpy())
+    print("builder_forward_600: edges", tuple(gph.edge_index.shape), "attr", tuple(gph.edge_attr.shape))
+
+    # ---- pretrain_step (models/dgdm_model.py:447-506) with the reference's own RNG order replayed:
+    # _apply_entity_masking: randperm(n)[:k], randn(F) mask token; then _compute_diffusion_loss: randint(B), per graph randn x2
+    torch.manual_seed(123)
+    rb = _to_ref(ns, b)
+    with torch.no_grad():
+        op = m.pretrain_step(rb, mask_ratio=0.15)
+    torch.manual_seed(123)
+    n = b.x.size(0)
+    k = int(n * 0.15)
+    mask_idx = torch.randperm(n)[:k]
+    mask_tok = torch.randn(b.x.size(1))
+    t = torch.randint(0, SMALL_CFG["num_diffusion_steps"], (2,))
+    noise, target = [], []
+    for sz in (150, 150):
+        noise.append(torch.randn(1, sz, 32)[0])
+        target.append(torch.randn(sz, 32))
+    np.savez_compressed(os.path.join(GOLDEN, "pretrain_step.npz"), mask_indices=mask_idx.numpy(), mask_token=mask_tok.numpy(),
+                        timesteps=t.numpy(), noise=torch.cat(noise).numpy(), target=torch.cat(target).numpy(),
+                        diffusion_loss=op["diffusion_loss"].numpy(), total_pretrain_loss=op["total_pretrain_loss"].numpy(),
+                        noisy_embeddings=op["noisy_embeddings"].numpy())
+    print("pretrain_step: loss", float(op["total_pretrain_loss"]))
+
+    # ---- public MultiHeadAttention.forward / SpatialAttention.forward (core/attention.py:73-181, 285-327)
+    att = m.spatial_attention.attention          # embed 32, 2 heads
+    torch.manual_seed(41)
+    q = torch.randn(2, 37, 32)
+    kx = torch.randn(2, 53, 32)
+    vx = torch.randn(2, 53, 32)
+    amask = torch.randn(37, 53) * 2.0
+    amask_sq = torch.randn(37, 37) * 2.0
+    kpm = torch.zeros(2, 53, dtype=torch.bool)
+    kpm[0, 40:] = True
+    kpm[1, :5] = True
+    mh = {}
+    with torch.no_grad():
+        o, w = att(q)
+        mh["self_out"], mh["self_w"] = o.numpy(), w.numpy()
+        o, w = att(q, attn_mask=amask_sq, average_attn_weights=False)
+        mh["selfmask_out"], mh["selfmask_w"] = o.numpy(), w.numpy()
+        o, w = att(q, kx, vx, key_padding_mask=kpm, attn_mask=amask)
+        mh["cross_out"], mh["cross_w"] = o.numpy(), w.numpy()
+        o, w = att(q, kx, need_weights=False)
+        mh["cross_kv_out"] = o.numpy()
+        xs_ = torch.randn(2, 45, 32)
+        ps_ = torch.rand(2, 45, 2) * 3.0
+        ps_[1] += 1.5                                  # different extents per batch element: the PE min/max is GLOBAL (:233-236)
+        o, w = m.spatial_attention(xs_, ps_)
+        mh["spatial_out"], mh["spatial_w"] = o.numpy(), w.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "mha_public.npz"), q=q.numpy(), k=kx.numpy(), v=vx.numpy(), attn_mask=amask.numpy(),
+                        attn_mask_sq=amask_sq.numpy(), key_padding_mask=kpm.numpy(), spatial_x=xs_.numpy(), spatial_pos=ps_.numpy(), **mh)
+    print("mha_public: ok")
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     ns = ref_loader.load()
     torch.set_num_threads(8)
+    if "--round2" in sys.argv:
+        return round2(ns)
 
     # ---- 1. small model, 2-graph batch: inference (+ stages via hooks) and pretrain with replayed RNG
     m = ref_model(ns, SMALL_CFG)

@@ -9,6 +9,8 @@ from dgdm_histopath_lab_b200 import synth
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 SMALL_CFG = dict(node_features=48, hidden_dims=[64, 32, 32], num_diffusion_steps=10, attention_heads=2, graph_layers=4,
                  num_classes=3, regression_targets=2)
+BUILDER_MODEL_CFG = dict(node_features=64, hidden_dims=[64, 32, 32], num_diffusion_steps=10, attention_heads=2, graph_layers=3,
+                         num_classes=3)
 BASE_CFG = dict(node_features=768, hidden_dims=[512, 256, 128], num_diffusion_steps=10, attention_heads=8, graph_layers=4)
 
 

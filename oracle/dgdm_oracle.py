@@ -42,10 +42,11 @@ def pad_edge_attr(edge_attr, num_edges, width, like):
 # ----------------------------------------------------------------------------- message passing
 def gcn_norm(edge_index, num_nodes, dtype=torch.float32):
     """core/graph_layers.py:76-84 with PyG add_self_loops/degree semantics (loops appended after the edges)."""
-    loops = torch.arange(num_nodes, dtype=edge_index.dtype)
+    dev = edge_index.device          # device / dtype follow the inputs: the tests also run this restatement in float64 on the GPU
+    loops = torch.arange(num_nodes, dtype=edge_index.dtype, device=dev)
     ei = torch.cat([edge_index, torch.stack([loops, loops])], dim=1)
     row, col = ei[0], ei[1]
-    deg = torch.zeros(num_nodes, dtype=dtype).index_add_(0, col, torch.ones(col.numel(), dtype=dtype))
+    deg = torch.zeros(num_nodes, dtype=dtype, device=dev).index_add_(0, col, torch.ones(col.numel(), dtype=dtype, device=dev))
     dinv = deg.pow(-0.5)
     dinv[dinv == float("inf")] = 0
     return ei, dinv[row] * dinv[col]
@@ -61,7 +62,7 @@ def graph_convolution(sd, p, x, edge_index, edge_attr=None):
         ea = torch.cat([edge_attr, edge_attr.new_zeros(n, edge_attr.size(1))], 0)
         msg = msg + F.linear(ea, sd[p + ".edge_lin.weight"])
     msg = norm.view(-1, 1) * msg
-    out = torch.zeros(n, h.size(1), dtype=h.dtype).index_add_(0, ei[1], msg)
+    out = torch.zeros(n, h.size(1), dtype=h.dtype, device=h.device).index_add_(0, ei[1], msg)
     if (p + ".bias") in sd:
         out = out + sd[p + ".bias"]
     return out
@@ -106,30 +107,34 @@ def adaptive_graph_pooling(sd, p, x, edge_index, edge_attr=None, ratio=0.5):
     mask[top] = True
     perm = mask.nonzero(as_tuple=False).squeeze(-1)
     px = x[perm] * s[perm].unsqueeze(-1)
-    node_map = torch.full((x.size(0),), -1, dtype=torch.long)
-    node_map[perm] = torch.arange(perm.size(0))
+    node_map = torch.full((x.size(0),), -1, dtype=torch.long, device=x.device)
+    node_map[perm] = torch.arange(perm.size(0), device=x.device)
     emask = (node_map[edge_index[0]] >= 0) & (node_map[edge_index[1]] >= 0)
     pei = node_map[edge_index[:, emask]]
     pea = edge_attr[emask] if edge_attr is not None else None
     return px, pei, pea, perm, s
 
 
-def graph_unet(sd, p, x, edge_index, edge_attr=None, depth=3, act="relu", return_perms=False):
-    """GraphUNet.forward, core/graph_layers.py:400-458 with P5 (edge_dim 32, up_convs on hidden); D8 kept."""
+def graph_unet(sd, p, x, edge_index, edge_attr=None, depth=3, act="relu", return_perms=False, scores_out=None):
+    """GraphUNet.forward, core/graph_layers.py:400-458 with P5 (edge_dim 32, up_convs on hidden); D8 kept.
+    scores_out (list): receives the tanh pooling scores of every level (for the top-k flip report)."""
     a = _act(act)
-    edge_attr = pad_edge_attr(edge_attr, edge_index.size(1), 32, x)
+    # None stays None below: edge_lin has no bias, so zeros(E,32) (P5) contribute exactly nothing
+    edge_attr = pad_edge_attr(edge_attr, edge_index.size(1), 32, x) if edge_attr is not None else None
     xs, eis, eas, perms = [], [edge_index], [edge_attr], []
     x = dynamic_graph_layer(sd, p + ".down_convs.0", x, edge_index, edge_attr)
     xs.append(x)
     for i in range(depth):
         x = dynamic_graph_layer(sd, f"{p}.down_convs.{i + 1}", a(x), eis[-1], eas[-1])
         xs.append(x)
-        x, ei, ea, perm, _ = adaptive_graph_pooling(sd, f"{p}.pools.{i}", x, eis[-1], eas[-1])
+        x, ei, ea, perm, sc = adaptive_graph_pooling(sd, f"{p}.pools.{i}", x, eis[-1], eas[-1])
         eis.append(ei); eas.append(ea); perms.append(perm)
+        if scores_out is not None:
+            scores_out.append(sc)
     x = dynamic_graph_layer(sd, p + ".bottom_conv", a(x), eis[-1], eas[-1])
     for i in range(depth):
         j = depth - 1 - i
-        up = torch.zeros(xs[j + 1].size(0), x.size(1), dtype=x.dtype)
+        up = torch.zeros(xs[j + 1].size(0), x.size(1), dtype=x.dtype, device=x.device)
         up[perms[j]] = x
         x = a(up + xs[j + 1])
         x = dynamic_graph_layer(sd, f"{p}.up_convs.{i}", x, eis[j + 1], eas[j + 1])   # D8: pooled edges, level-j nodes

@@ -330,6 +330,35 @@ class DGDMModel(nn.Module):
         except Exception as e:
             raise ModelInferenceError(f"Forward pass failed: {e}") from e
 
+    def graphed(self, data, mode="inference", return_embeddings=False, warmup=2):
+        """CUDA-graph replay of `forward(data, mode, return_embeddings=...)` for small graphs, where the ~150 kernel launches and
+        ~100 ctypes calls of a forward cost more than the kernels (host-bound below ~10k nodes). The forward is validated and
+        warmed up eagerly (weight images, CSR, kernel attributes), captured once, and the returned callable replays it:
+        `run = model.graphed(d); out = run()` — `out` tensors are static buffers overwritten by the next replay; the graph reads
+        `data.x` / `data.pos` / `data.edge_attr` in place, so new features may be copied into those tensors between replays
+        (same graph structure). Single-GPU inference / finetune only."""
+        if self._comm is not None or mode == "pretrain":
+            raise ModelInferenceError("graphed() supports single-GPU inference / finetune forwards")
+        for _ in range(max(1, warmup)):
+            self.forward(data, mode, False, return_embeddings)
+        versions = self._weights_version()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_out = self.forward(data, mode, False, return_embeddings, validate=False)
+        model = self
+
+        def run():
+            if model._weights_version() != versions:
+                raise ModelInferenceError("parameters changed since graphed() captured the forward: capture again")
+            graph.replay()
+            return static_out
+        run.graph, run.outputs = graph, static_out
+        return run
+
+    def _weights_version(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
     def _num_nodes(self, data):
         """N of the whole batch: x may hold only the owned rows of a node-partitioned graph."""
         if self._comm is None:

@@ -28,7 +28,10 @@ import sys
 import torch
 import torch.nn as nn
 
+_HERE = os.path.dirname(os.path.abspath(__file__))
 REF_ROOT = os.environ.get("DGDM_REFERENCE_ROOT", "/root/reference")
+if not os.path.isdir(os.path.join(REF_ROOT, "dgdm_histopath")):
+    REF_ROOT = os.path.join(_HERE, "_ref")          # the copy staged by oracle/stage_ref.py (travels to the GPU box)
 SHIM_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "refshim")
 ALL_PATCHES = ("P1", "P2", "P3", "P4", "P5", "P6", "P7")
 
@@ -37,6 +40,18 @@ _state = {}
 
 def available():
     return os.path.isdir(os.path.join(REF_ROOT, "dgdm_histopath"))
+
+
+def is_live_tree():
+    """True when REF_ROOT is the read-only reference checkout itself (build container), False for the staged copy."""
+    return available() and os.path.abspath(REF_ROOT) != os.path.abspath(os.path.join(_HERE, "_ref"))
+
+
+def set_monitor_stub(stub):
+    """Switch the reference's `monitor_operation` (utils/monitoring.py:479: psutil sampling + gc.collect() around every stage,
+    about half of its forward time at 2k nodes) between as-shipped (False) and a no-op (True) after load()."""
+    mdl, orig, noop = _state["monitor"]
+    mdl.monitor_operation = noop if stub else orig
 
 
 def _pad_cols(t, width):
@@ -69,10 +84,11 @@ def load(patches=ALL_PATCHES, stub_monitor=True):
         tgb = importlib.import_module("dgdm_histopath.preprocessing.tissue_graph_builder")
         sp = importlib.import_module("dgdm_histopath.preprocessing.slide_processor")
 
+    @contextlib.contextmanager
+    def _noop(*a, **k):
+        yield
+    _state["monitor"] = (mdl, mdl.monitor_operation, _noop)
     if stub_monitor:
-        @contextlib.contextmanager
-        def _noop(*a, **k):
-            yield
         mdl.monitor_operation = _noop
 
     if "P2" in patches:

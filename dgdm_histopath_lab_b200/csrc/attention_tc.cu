@@ -16,6 +16,7 @@
 // explicit row-max pass (and an O/l rescale through tcgen05.ld/st) is needed at all; the common path is add, add, exp2, add, split.
 // Roofline: MUFU-bound (one exp2 per score + one sqrt per (row,key) per head group = 1.25 MUFU/score at 16 lanes/clk/SM).
 #include "tc05.cuh"
+#include <cstdlib>
 
 namespace dgdm {
 
@@ -465,6 +466,312 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc_kernel(const At
   if (warp == 10) tmem_dealloc(tm, 512);
 }
 
+
+// ---------------------------------------------------------------------------------------------- 16-softmax-warp variant
+// Same arithmetic, data layout and MMA schedule as spatial_attn_tc_kernel, but 4 softmax warps per scheduler instead of 2: the
+// round-1 capture showed the two 216-register warps of a scheduler latency-bound (issue 53 %, XU 64 %, "wait" the top stall), i.e.
+// neither the issue slots nor the MUFU pipe could be kept busy by two in-order instruction streams. Here a softmax thread owns
+// (query row, 4 heads, 32 of the block's 64 keys): 16 softmax warps = {head group g} x {key half kh} x {row quarter}, 112 registers
+// each, processing 16-key quarters (one K-step of the PV MMA) so that the TMEM read of the next quarter overlaps the exp2 phase.
+// The two threads that share a (row, head) keep IDENTICAL lazy reference maxima: the decision to refresh depends only on values both
+// hold, and the refreshed maximum is exchanged through shared memory under a 64-thread named barrier (rare path).
+constexpr int T16_THREADS = 640;                // 16 softmax warps + {MMA 0, MMA 1, loader, idle}
+constexpr int T16_XCH = 8192;                   // need-exchange [2 buf][2 g][2 kh][128] floats + epilogue l exchange [2 g][128][4]
+constexpr int T16_SMEM = TC_SMEM + T16_XCH;
+#ifndef T16_MMA_SLEEP_NS
+#define T16_MMA_SLEEP_NS 32
+#endif
+
+__global__ void __launch_bounds__(T16_THREADS, 1) spatial_attn_tc16_kernel(const AttnTcParams p) {
+  using namespace tc;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* bp = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bars = base + TC_STAGES * TC_IMG;
+  const uint32_t bar_full = bars, bar_empty = bars + 24, bar_S = bars + 48, bar_P = bars + 80, bar_O = bars + 112, bar_Q = bars + 128;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bp + TC_STAGES * TC_IMG + 192);
+  float* xch = reinterpret_cast<float*>(bp + TC_STAGES * TC_IMG + 1024 + 256);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int seg = -1, row0 = 0;
+  {
+    int acc = 0;
+    for (int s = 0; s < p.num_seg; ++s) {
+      const int a = p.qseg[s], b = p.qseg[s + 1];
+      const int nt = (b - a + TC_QT - 1) / TC_QT;
+      if ((int)blockIdx.x < acc + nt) { seg = s; row0 = a + ((int)blockIdx.x - acc) * TC_QT; break; }
+      acc += nt;
+    }
+  }
+  if (seg < 0) return;
+  const int qend = p.qseg[seg + 1];
+  const int split = blockIdx.y;
+  const int nb_seg = p.blk_ptr[seg + 1] - p.blk_ptr[seg];
+  const int per = (nb_seg + p.nsplit - 1) / p.nsplit;
+  const int b_lo = min(nb_seg, split * per), b_hi = min(nb_seg, b_lo + per);
+  const int nblk = b_hi - b_lo;
+  const uint8_t* img0 = p.img + (size_t)(p.blk_ptr[seg] + b_lo) * TC_IMG;
+
+  if (tid == 0) {
+    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 2 + 16); }
+    for (int i = 0; i < 4; ++i) { mbar_init(bar_S + 8 * i, 1); mbar_init(bar_P + 8 * i, 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_O + 8 * i, 1); mbar_init(bar_Q + 8 * i, 4); }
+    mbar_fence_init();
+  }
+  if (warp == 18) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tm = *tmem_slot;
+
+  if (warp < 16) {
+    // =========================================================================== softmax warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    const int wq = warp & 3, g = warp >> 3, kh = (warp >> 2) & 1;
+    const int rl = wq * 32 + lane;                                  // row inside the tile
+    const int row = row0 + rl;
+    const bool rvalid = row < qend;
+    const uint32_t trow = tm + ((uint32_t)(wq * 32) << 16);
+    const int bar_id = 1 + g * 4 + wq;                              // named barrier of the two key halves of this (g, row quarter)
+    float qn[4];
+    {
+      const float* qp = p.q_qkv + (size_t)(rvalid ? row : row0) * p.ld_q + 64 * g;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t qh[8], ql[8];
+        float sq = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float4 v = ldg4(qp + 16 * i + 4 * c);
+          if (!rvalid) v = make_float4(0.f, 0.f, 0.f, 0.f);
+          v.x *= p.qscale; v.y *= p.qscale; v.z *= p.qscale; v.w *= p.qscale;
+          sq += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+          split_pack(v.x, v.y, qh[2 * c], ql[2 * c]);
+          split_pack(v.z, v.w, qh[2 * c + 1], ql[2 * c + 1]);
+        }
+        qn[i] = sqrtf(sq) * 1.0001f;
+        if (kh == 0) {
+          tmem_st8_nowait(trow + tc_qhi(4 * g + i), qh);
+          tmem_st8_nowait(trow + tc_qlo(4 * g + i), ql);
+        }
+      }
+      if (kh == 0) {
+        tmem_wait_st();
+        fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_Q + 8 * g);
+      }
+    }
+    float qx = 0.f, qy = 0.f;
+    if (p.q_pos != nullptr && rvalid) { qx = p.q_pos[2 * (size_t)row] * p.pscale; qy = p.q_pos[2 * (size_t)row + 1] * p.pscale; }
+
+    float m[4];
+    unsigned long long lsum[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { m[i] = -INFINITY; lsum[i] = 0ull; }
+    int nx = 0;                                                      // need-exchange counter (buffer parity)
+
+    uint32_t ra[16], rb[16];                                         // keys [32 kh, 32 kh + 16) and [32 kh + 16, 32 kh + 32) of the unit
+    const int total = 4 * nblk;
+    const uint32_t kcol = (uint32_t)(32 * kh);
+    if (nblk > 0) {
+      mbar_wait_parked(bar_S + 8 * (2 * g), 0);
+      fence_after();
+      tmem_ld16_nowait(trow + tc_slot(g, 0) + kcol, ra);
+      tmem_ld16_nowait(trow + tc_slot(g, 0) + kcol + 16, rb);
+    }
+    const unsigned long long neg1 = pk2(-1.0f, -1.0f);
+    // exp2 + fp16 hi/lo split of one 16-key quarter held in r (in place: r[0..7] = hi, r[8..15] = lo), accumulating the row sum
+    auto softmax_q = [&](uint32_t* r, const unsigned long long* nbc, unsigned long long nmu2, unsigned long long& ls) {
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const unsigned long long x = add2(add2(pk2(__uint_as_float(r[2 * t]), __uint_as_float(r[2 * t + 1])), nbc[t]), nmu2);
+        const float p0 = tc_ex2(lo32(x)), p1 = tc_ex2(hi32(x));
+        const unsigned long long pp = pk2(p0, p1);
+        ls = add2(ls, pp);
+        const float h0 = __uint_as_float(__float_as_uint(p0) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(p1) & 0xffffe000u);
+        const unsigned long long ll = fma2(pk2(h0, h1), neg1, pp);
+        hi[t] = tc_pack_h2(h0, h1);
+        lo[t] = tc_pack_h2(lo32(ll), hi32(ll));
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { r[t] = hi[t]; r[8 + t] = lo[t]; }
+    };
+
+    for (int j = 0; j < nblk; ++j) {
+      const int st = j % TC_STAGES;
+      mbar_wait_parked(bar_full + 8 * st, (uint32_t)((j / TC_STAGES) & 1));
+      unsigned long long nb[16];                                      // negated distance bias of this row against my 32 keys
+      float kmax[4];
+      {
+        const float* kp = reinterpret_cast<const float*>(bp + st * TC_IMG + TC_OFF_POS) + 32 * kh;
+        const unsigned long long qx2 = pk2(qx, qx), qy2 = pk2(qy, qy);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const float4 kx = *reinterpret_cast<const float4*>(kp + 4 * t);
+          const float4 ky = *reinterpret_cast<const float4*>(kp + TC_BN + 4 * t);
+          unsigned long long dx = sub2(qx2, pk2(kx.x, kx.y)), dy = sub2(qy2, pk2(ky.x, ky.y));
+          unsigned long long d2 = fma2(dx, dx, mul2(dy, dy));
+          nb[2 * t] = pk2(-tc_sqrt(lo32(d2)), -tc_sqrt(hi32(d2)));
+          dx = sub2(qx2, pk2(kx.z, kx.w)); dy = sub2(qy2, pk2(ky.z, ky.w));
+          d2 = fma2(dx, dx, mul2(dy, dy));
+          nb[2 * t + 1] = pk2(-tc_sqrt(lo32(d2)), -tc_sqrt(hi32(d2)));
+        }
+        const float4 km = *reinterpret_cast<const float4*>(bp + st * TC_IMG + TC_OFF_KMAX + 16 * g);
+        kmax[0] = km.x; kmax[1] = km.y; kmax[2] = km.z; kmax[3] = km.w;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_empty + 8 * st);
+
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int u = 4 * j + i, s = u & 1;
+        const uint32_t slot = trow + tc_slot(g, s) + kcol;
+        const uint32_t nslot = trow + tc_slot(g, s ^ 1) + kcol;
+        tmem_wait_ld();
+        const bool need = (j == 0) || (qn[i] * kmax[i] > m[i] + TC_TAU);
+        if (__any_sync(0xffffffffu, need)) {
+          float rmax = -INFINITY;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const unsigned long long xa = add2(pk2(__uint_as_float(ra[2 * t]), __uint_as_float(ra[2 * t + 1])), nb[t]);
+            const unsigned long long xb = add2(pk2(__uint_as_float(rb[2 * t]), __uint_as_float(rb[2 * t + 1])), nb[8 + t]);
+            rmax = fmaxf(rmax, fmaxf(fmaxf(lo32(xa), hi32(xa)), fmaxf(lo32(xb), hi32(xb))));
+          }
+          // the other key half of this (row, head) takes the same branch (same qn, kmax, m): exchange the partial maxima
+          float* xb_ = xch + (((nx & 1) * 2 + g) * 2) * 128;
+          xb_[kh * 128 + rl] = rmax;
+          named_bar_sync(bar_id, 64);
+          rmax = fmaxf(rmax, xb_[(kh ^ 1) * 128 + rl]);
+          ++nx;
+          float sc = 1.0f;
+          if (j == 0) m[i] = rmax;
+          else if (rmax > m[i] + TC_TAU) { sc = tc_ex2(m[i] - rmax); m[i] = rmax; }
+          if (__any_sync(0xffffffffu, sc != 1.0f)) {
+            if (kh == 0) {                                            // O_h of this row is rescaled once, by the kh = 0 thread
+              uint32_t o[16];
+              tmem_ld16_nowait(trow + tc_ocol(4 * g + i), o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int t = 0; t < 16; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) * sc);
+              tmem_st16_nowait(trow + tc_ocol(4 * g + i), o);
+            }
+            lsum[i] = mul2(lsum[i], pk2(sc, sc));
+          }
+        }
+        const float mu = (m[i] == -INFINITY) ? 0.f : m[i];
+        const unsigned long long nmu2 = pk2(-mu, -mu);
+        softmax_q(ra, nb, nmu2, lsum[i]);
+        tmem_st16_nowait(slot, ra);
+        if (u + 1 < total) {                                          // prefetch the first quarter of the next unit's S into ra
+          mbar_wait_parked(bar_S + 8 * (2 * g + (s ^ 1)), (uint32_t)(((u + 1) >> 1) & 1));
+          fence_after();
+          tmem_ld16_nowait(nslot, ra);
+        }
+        softmax_q(rb, nb + 8, nmu2, lsum[i]);
+        tmem_st16_nowait(slot + 16, rb);
+        tmem_wait_st();
+        fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_P + 8 * (2 * g + s));
+        if (u + 1 < total) tmem_ld16_nowait(nslot + 16, rb);
+      }
+    }
+    // ---- epilogue: unnormalised O (each key-half warp stores 32 of the group's 64 columns), reference max m, row sum l
+    if (nblk > 0) { mbar_wait_parked(bar_O + 8 * g, 0); fence_after(); }
+    float* lx = xch + 1024 + (g * 128 + rl) * 4;
+    if (kh == 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) lx[i] = lo32(lsum[i]) + hi32(lsum[i]);
+    }
+    named_bar_sync(bar_id, 64);
+    const size_t prow = (size_t)split * p.Nq + (size_t)row;
+    {
+      uint32_t r[32];
+      if (nblk > 0) { tmem_ld32_nowait(trow + tc_ocol(4 * g) + 32 * kh, r); tmem_wait_ld(); }
+      else {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) r[t] = 0u;
+      }
+      if (rvalid) {
+        float* op = p.Opart + prow * 128 + 64 * g + 32 * kh;
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+          *reinterpret_cast<float4*>(op + 4 * t) = make_float4(__uint_as_float(r[4 * t]), __uint_as_float(r[4 * t + 1]),
+                                                               __uint_as_float(r[4 * t + 2]), __uint_as_float(r[4 * t + 3]));
+      }
+    }
+    if (rvalid && kh == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        p.Mpart[prow * 8 + 4 * g + i] = m[i];
+        p.Lpart[prow * 8 + 4 * g + i] = (lo32(lsum[i]) + hi32(lsum[i])) + lx[i];
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    if (warp < 18) {
+    // =========================================================================== MMA issuers (one per head group)
+    const int g = warp - 16;
+    if (nblk > 0 && elect_one()) {
+      const uint32_t id64 = idesc_f16(128, 64), id16 = idesc_f16(128, 16);
+      const int total = 4 * nblk;
+      mbar_wait_sleep(bar_Q + 8 * g, 0, T16_MMA_SLEEP_NS);
+      fence_after();
+      auto issue_qk = [&](int u) {
+        const int b = u >> 2, i = u & 3, st = b % TC_STAGES;
+        if (i == 0) { mbar_wait_sleep(bar_full + 8 * st, (uint32_t)((b / TC_STAGES) & 1), T16_MMA_SLEEP_NS); fence_after(); }
+        const uint32_t d = tm + tc_slot(g, u & 1);
+        const uint32_t kb = base + st * TC_IMG + 8192 * g + 32 * i;
+        mma_ts(d, tm + tc_qhi(4 * g + i), desc_sw128(kb), id64, 0);
+        mma_ts(d, tm + tc_qlo(4 * g + i), desc_sw128(kb), id64, 1);
+        mma_ts(d, tm + tc_qhi(4 * g + i), desc_sw128(kb + 16384), id64, 1);
+        mma_commit(bar_S + 8 * (2 * g + (u & 1)));
+      };
+      issue_qk(0);
+      if (total > 1) issue_qk(1);
+      for (int u = 0; u < total; ++u) {
+        const int b = u >> 2, i = u & 3, st = b % TC_STAGES, h = 4 * g + i;
+        mbar_wait_sleep(bar_P + 8 * (2 * g + (u & 1)), (uint32_t)((u >> 1) & 1), T16_MMA_SLEEP_NS);
+        fence_after();
+        const uint32_t vb = base + st * TC_IMG + TC_OFF_V + 2048 * h;
+        const uint32_t ps = tm + tc_slot(g, u & 1);
+        const uint32_t od = tm + tc_ocol(h);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          mma_ts(od, ps + 16 * ks, desc_sw128(vb + 32 * ks), id16, (b > 0 || ks > 0) ? 1u : 0u);
+          mma_ts(od, ps + 16 * ks + 8, desc_sw128(vb + 32 * ks), id16, 1);
+          mma_ts(od, ps + 16 * ks, desc_sw128(vb + 16384 + 32 * ks), id16, 1);
+        }
+        if (i == 3) mma_commit(bar_empty + 8 * st);
+        if (u + 2 < total) issue_qk(u + 2);
+      }
+      mma_commit(bar_O + 8 * g);
+    }
+    __syncwarp();
+    } else if (warp == 18) {
+    // =========================================================================== loader (cp.async.bulk, 3-stage ring)
+    if (elect_one()) {
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j % TC_STAGES;
+        mbar_wait_sleep(bar_empty + 8 * st, (uint32_t)(((j / TC_STAGES) & 1) ^ 1), 128);
+        mbar_arrive_expect_tx(bar_full + 8 * st, TC_IMG_USED);
+        const uint8_t* src = img0 + (size_t)j * TC_IMG;
+        const uint32_t dst = base + st * TC_IMG;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) bulk_g2s(dst + 16384 * c, src + 16384 * c, 16384, bar_full + 8 * st);
+        bulk_g2s(dst + 65536, src + 65536, TC_IMG_USED - 65536, bar_full + 8 * st);
+      }
+    }
+    __syncwarp();
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 18) tmem_dealloc(tm, 512);
+}
+
 static inline size_t tc_al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // Key splits per query tile. Two constraints: (1) occupancy — at least ~8 CTAs of work per SM; (2) ACCURACY — the tensor core
@@ -522,15 +829,18 @@ int attn_tc_launch(const float* q_qkv, int ld_q, const float* q_pos, const int* 
   attn_tc_prep_kernel<<<(unsigned)nblk_max, 256, 0, s>>>(kv_qkv, ld_kv, kv_pos, kseg_ptr, blk_ptr, num_seg, pscale, img);
   static PerDeviceOnce attr_set;
   if (attr_set.needed()) {
-    if (cudaFuncSetAttribute(spatial_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM) != cudaSuccess) return DGDM_ERR_LAUNCH;
+    if (cudaFuncSetAttribute(spatial_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(spatial_attn_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T16_SMEM) != cudaSuccess) return DGDM_ERR_LAUNCH;
     attr_set.mark();
   }
+  static const int variant = [] { const char* e = getenv("DGDM_ATTN_TC_WARPS"); return e ? atoi(e) : 16; }();
   AttnTcParams p;
   p.q_qkv = q_qkv; p.ld_q = ld_q; p.q_pos = q_pos; p.qseg = qseg_ptr; p.kseg = kseg_ptr; p.num_seg = num_seg; p.Nq = Nq; p.nsplit = ns;
   p.img = img; p.blk_ptr = blk_ptr; p.qscale = LOG2E / 4.0f; p.pscale = pscale;
   p.Opart = Opart; p.Mpart = Mpart; p.Lpart = Lpart;
   const int tiles = (Nq + TC_QT - 1) / TC_QT + num_seg;
-  spatial_attn_tc_kernel<<<dim3(tiles, ns, 1), TC_THREADS, TC_SMEM, s>>>(p);
+  if (variant == 8) spatial_attn_tc_kernel<<<dim3(tiles, ns, 1), TC_THREADS, TC_SMEM, s>>>(p);
+  else spatial_attn_tc16_kernel<<<dim3(tiles, ns, 1), T16_THREADS, T16_SMEM, s>>>(p);
   attn_launch_combine(Opart, Mpart, Lpart, ns, Nq, D, heads, out, ldo, s);
   if (cudaGetLastError() != cudaSuccess) return DGDM_ERR_LAUNCH;
   return DGDM_OK;

@@ -77,6 +77,17 @@ __device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) 
   }
 }
 
+// Poll + fixed sleep: for the single-thread roles (MMA issuer, bulk-copy loader). NANOSLEEP.SYNCS (what the suspend-hint form
+// compiles to) is woken by EVERY mbarrier event of the CTA — measured ~13 spurious wake-ups (x5 instructions) per wait in the
+// attention kernel, 8 % of all issue slots — a plain nanosleep is not.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t spins = 0;
+  while (!mbar_test_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (++spins > (1u << 24)) { asm volatile("trap;"); }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -44,7 +44,10 @@ struct AttnTcParams {
   const uint8_t* img; const int* blk_ptr;
   float qscale, pscale;
   float* Opart; float* Mpart; float* Lpart;
+  int mma_sleep_ns;            // single-thread roles (MMA issuers, loader): 0 = parked mbarrier waits, > 0 = poll + nanosleep
 };
+// wait of a single-thread role
+#define TC_ROLE_WAIT(bar, par) do { if (p.mma_sleep_ns > 0) mbar_wait_sleep((bar), (par), (uint32_t)p.mma_sleep_ns); else mbar_wait_parked((bar), (par)); } while (0)
 
 // ---------------------------------------------------------------------------------------------- packed fp32x2 helpers
 __device__ __forceinline__ unsigned long long pk2(float a, float b) {
@@ -411,11 +414,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc_kernel(const At
     if (nblk > 0 && elect_one()) {
       const uint32_t id64 = idesc_f16(128, 64), id16 = idesc_f16(128, 16);
       const int total = 4 * nblk;
-      mbar_wait_parked(bar_Q + 8 * g, 0);
+      TC_ROLE_WAIT(bar_Q + 8 * g, 0);
       fence_after();
       auto issue_qk = [&](int u) {
         const int b = u >> 2, i = u & 3, st = b % TC_STAGES;
-        if (i == 0) { mbar_wait_parked(bar_full + 8 * st, (uint32_t)((b / TC_STAGES) & 1)); fence_after(); }
+        if (i == 0) { TC_ROLE_WAIT(bar_full + 8 * st, (uint32_t)((b / TC_STAGES) & 1)); fence_after(); }
         const uint32_t d = tm + tc_slot(g, u & 1);
         const uint32_t kb = base + st * TC_IMG + 8192 * g + 32 * i;
         mma_ts(d, tm + tc_qhi(4 * g + i), desc_sw128(kb), id64, 0);
@@ -427,7 +430,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc_kernel(const At
       if (total > 1) issue_qk(1);
       for (int u = 0; u < total; ++u) {
         const int b = u >> 2, i = u & 3, st = b % TC_STAGES, h = 4 * g + i;
-        mbar_wait_parked(bar_P + 8 * (2 * g + (u & 1)), (uint32_t)((u >> 1) & 1));
+        TC_ROLE_WAIT(bar_P + 8 * (2 * g + (u & 1)), (uint32_t)((u >> 1) & 1));
         fence_after();
         const uint32_t vb = base + st * TC_IMG + TC_OFF_V + 2048 * h;
         const uint32_t ps = tm + tc_slot(g, u & 1);
@@ -449,7 +452,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc_kernel(const At
     if (elect_one()) {
       for (int j = 0; j < nblk; ++j) {
         const int st = j % TC_STAGES;
-        mbar_wait_parked(bar_empty + 8 * st, (uint32_t)(((j / TC_STAGES) & 1) ^ 1));
+        TC_ROLE_WAIT(bar_empty + 8 * st, (uint32_t)(((j / TC_STAGES) & 1) ^ 1));
         mbar_arrive_expect_tx(bar_full + 8 * st, TC_IMG_USED);
         const uint8_t* src = img0 + (size_t)j * TC_IMG;
         const uint32_t dst = base + st * TC_IMG;
@@ -468,6 +471,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc_kernel(const At
 
 
 // ---------------------------------------------------------------------------------------------- 16-softmax-warp variant
+// MEASURED SLOWER than the 8-warp kernel (38.3 vs 35.7 ms at 100k nodes, profiles/attn_tc16_r02b.txt) and therefore NOT the default
+// (DGDM_ATTN_TC_WARPS=16 selects it): the kernel is not latency-bound. tools/mufu_probe.cu shows that the softmax instruction mix
+// itself (per two scores: 2 MUFU.EX2, 3 FADD2, 2 LOP3, 1 FFMA2, 2 F2FP) sustains only 24.5 / 22.0 / 21.4 cycles per pair at 2 / 4 / 8
+// warps per scheduler against the 16-cycle MUFU ideal — the packed-fp32 and conversion instructions co-limit with the XU pipe — so
+// doubling the warps buys at most 10 % while halving the keys per thread doubles the per-unit synchronisation overhead.
 // Same arithmetic, data layout and MMA schedule as spatial_attn_tc_kernel, but 4 softmax warps per scheduler instead of 2: the
 // round-1 capture showed the two 216-register warps of a scheduler latency-bound (issue 53 %, XU 64 %, "wait" the top stall), i.e.
 // neither the issue slots nor the MUFU pipe could be kept busy by two in-order instruction streams. Here a softmax thread owns
@@ -717,11 +725,11 @@ __global__ void __launch_bounds__(T16_THREADS, 1) spatial_attn_tc16_kernel(const
     if (nblk > 0 && elect_one()) {
       const uint32_t id64 = idesc_f16(128, 64), id16 = idesc_f16(128, 16);
       const int total = 4 * nblk;
-      mbar_wait_sleep(bar_Q + 8 * g, 0, T16_MMA_SLEEP_NS);
+      TC_ROLE_WAIT(bar_Q + 8 * g, 0);
       fence_after();
       auto issue_qk = [&](int u) {
         const int b = u >> 2, i = u & 3, st = b % TC_STAGES;
-        if (i == 0) { mbar_wait_sleep(bar_full + 8 * st, (uint32_t)((b / TC_STAGES) & 1), T16_MMA_SLEEP_NS); fence_after(); }
+        if (i == 0) { TC_ROLE_WAIT(bar_full + 8 * st, (uint32_t)((b / TC_STAGES) & 1)); fence_after(); }
         const uint32_t d = tm + tc_slot(g, u & 1);
         const uint32_t kb = base + st * TC_IMG + 8192 * g + 32 * i;
         mma_ts(d, tm + tc_qhi(4 * g + i), desc_sw128(kb), id64, 0);
@@ -733,7 +741,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) spatial_attn_tc16_kernel(const
       if (total > 1) issue_qk(1);
       for (int u = 0; u < total; ++u) {
         const int b = u >> 2, i = u & 3, st = b % TC_STAGES, h = 4 * g + i;
-        mbar_wait_sleep(bar_P + 8 * (2 * g + (u & 1)), (uint32_t)((u >> 1) & 1), T16_MMA_SLEEP_NS);
+        TC_ROLE_WAIT(bar_P + 8 * (2 * g + (u & 1)), (uint32_t)((u >> 1) & 1));
         fence_after();
         const uint32_t vb = base + st * TC_IMG + TC_OFF_V + 2048 * h;
         const uint32_t ps = tm + tc_slot(g, u & 1);
@@ -755,7 +763,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) spatial_attn_tc16_kernel(const
     if (elect_one()) {
       for (int j = 0; j < nblk; ++j) {
         const int st = j % TC_STAGES;
-        mbar_wait_sleep(bar_empty + 8 * st, (uint32_t)(((j / TC_STAGES) & 1) ^ 1), 128);
+        TC_ROLE_WAIT(bar_empty + 8 * st, (uint32_t)(((j / TC_STAGES) & 1) ^ 1));
         mbar_arrive_expect_tx(bar_full + 8 * st, TC_IMG_USED);
         const uint8_t* src = img0 + (size_t)j * TC_IMG;
         const uint32_t dst = base + st * TC_IMG;
@@ -833,7 +841,9 @@ int attn_tc_launch(const float* q_qkv, int ld_q, const float* q_pos, const int* 
         cudaFuncSetAttribute(spatial_attn_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T16_SMEM) != cudaSuccess) return DGDM_ERR_LAUNCH;
     attr_set.mark();
   }
-  static const int variant = [] { const char* e = getenv("DGDM_ATTN_TC_WARPS"); return e ? atoi(e) : 16; }();
+  static const int variant = [] { const char* e = getenv("DGDM_ATTN_TC_WARPS"); return e ? atoi(e) : 8; }();
+  static const int sleep_ns = [] { const char* e = getenv("DGDM_ATTN_TC_SLEEP"); return e ? atoi(e) : 0; }();
+  p.mma_sleep_ns = sleep_ns;
   AttnTcParams p;
   p.q_qkv = q_qkv; p.ld_q = ld_q; p.q_pos = q_pos; p.qseg = qseg_ptr; p.kseg = kseg_ptr; p.num_seg = num_seg; p.Nq = Nq; p.nsplit = ns;
   p.img = img; p.blk_ptr = blk_ptr; p.qscale = LOG2E / 4.0f; p.pscale = pscale;

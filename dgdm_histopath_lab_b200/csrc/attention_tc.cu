@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc_kernel(const At
 
 
 // ---------------------------------------------------------------------------------------------- 16-softmax-warp variant
-// MEASURED SLOWER than the 8-warp kernel (38.3 vs 35.7 ms at 100k nodes, profiles/attn_tc16_r02b.txt) and therefore NOT the default
+// MEASURED SLOWER than the 8-warp kernel (37.5 vs 35.9 ms at 100k nodes, profiles/attn_tc16_r02b.txt, profiles/mufu_probe_r02.txt) and therefore NOT the default
 // (DGDM_ATTN_TC_WARPS=16 selects it): the kernel is not latency-bound. tools/mufu_probe.cu shows that the softmax instruction mix
 // itself (per two scores: 2 MUFU.EX2, 3 FADD2, 2 LOP3, 1 FFMA2, 2 F2FP) sustains only 24.5 / 22.0 / 21.4 cycles per pair at 2 / 4 / 8
 // warps per scheduler against the 16-cycle MUFU ideal — the packed-fp32 and conversion instructions co-limit with the XU pipe — so
@@ -843,11 +843,11 @@ int attn_tc_launch(const float* q_qkv, int ld_q, const float* q_pos, const int* 
   }
   static const int variant = [] { const char* e = getenv("DGDM_ATTN_TC_WARPS"); return e ? atoi(e) : 8; }();
   static const int sleep_ns = [] { const char* e = getenv("DGDM_ATTN_TC_SLEEP"); return e ? atoi(e) : 0; }();
-  p.mma_sleep_ns = sleep_ns;
   AttnTcParams p;
   p.q_qkv = q_qkv; p.ld_q = ld_q; p.q_pos = q_pos; p.qseg = qseg_ptr; p.kseg = kseg_ptr; p.num_seg = num_seg; p.Nq = Nq; p.nsplit = ns;
   p.img = img; p.blk_ptr = blk_ptr; p.qscale = LOG2E / 4.0f; p.pscale = pscale;
   p.Opart = Opart; p.Mpart = Mpart; p.Lpart = Lpart;
+  p.mma_sleep_ns = sleep_ns;
   const int tiles = (Nq + TC_QT - 1) / TC_QT + num_seg;
   if (variant == 8) spatial_attn_tc_kernel<<<dim3(tiles, ns, 1), TC_THREADS, TC_SMEM, s>>>(p);
   else spatial_attn_tc16_kernel<<<dim3(tiles, ns, 1), T16_THREADS, T16_SMEM, s>>>(p);

@@ -309,32 +309,71 @@ class GraphUNet(nn.Module):
             return g[min(lvl_part.a, csr.N):min(lvl_part.b, csr.N)]
 
         a = self.act_name
-        csrs, xs, maps, perms, parts = [csr0], [], [], [], [part]
-        aggs = [agg_of(csr0, part, csr0.N)]
-        x = self.down_convs[0](x, ctx=csrs[0], agg_attr=aggs[0], part=parts[0])
+        if part is not None:
+            x = self._forward_partitioned(x, ctx, csr0, ea, part, a)
+            out = ops.linear(x, split_weight(self.final_conv.weight), self.final_conv.bias.detach())
+            return (out, self._last_perms) if return_perms else out
+        csrs, xs, maps, perms = [csr0], [], [], []
+        aggs = [agg_of(csr0, None, csr0.N)]
+        x = self.down_convs[0](x, ctx=csrs[0], agg_attr=aggs[0])
         xs.append(x)
         # `cur` is act(x) of the reference (:419/:432) — for level 0 applied by a tiny un-pool kernel with an empty map
         cur = ops.unpool_add_act(x, x, _neg_map(x), act=a)
         for i in range(self.depth):
-            x = self.down_convs[i + 1](cur, ctx=csrs[-1], agg_attr=aggs[-1], part=parts[-1])
+            x = self.down_convs[i + 1](cur, ctx=csrs[-1], agg_attr=aggs[-1])
             xs.append(x)
-            cur, pcsr, perm, node_map, _, ppart = self.pools[i].pool(x, csrs[-1], act=a, part=parts[-1],
-                                                                     with_eid=ea is not None)                # pooled + activated
-            csrs.append(pcsr); maps.append(node_map); perms.append(perm); parts.append(ppart)
-            aggs.append(agg_of(pcsr, ppart, pcsr.N))
-        x = self.bottom_conv(cur, ctx=csrs[-1], agg_attr=aggs[-1], part=parts[-1])
+            cur, pcsr, perm, node_map, _, _ = self.pools[i].pool(x, csrs[-1], act=a, with_eid=ea is not None)   # pooled + activated
+            csrs.append(pcsr); maps.append(node_map); perms.append(perm)
+            aggs.append(agg_of(pcsr, None, pcsr.N))
+        x = self.bottom_conv(cur, ctx=csrs[-1], agg_attr=aggs[-1])
         for i in range(self.depth):
             j = self.depth - 1 - i
-            nm = maps[j]
-            if part is not None:      # owned rows of level j; a kept node lives on the same rank at level j+1
-                nm = parts[j].local(nm)
-                nm = torch.where(nm >= 0, nm - parts[j + 1].a, nm).contiguous()
-            cur = ops.unpool_add_act(xs[j + 1], x, nm, act=a)
+            cur = ops.unpool_add_act(xs[j + 1], x, maps[j], act=a)
             # D8: level-(j+1) edges and attributes on the level-j node set; rows beyond the pooled CSR have no in-edges
-            agg_j = agg_of(csrs[j + 1], parts[j], csrs[j + 1].N) if part is not None else aggs[j + 1]
-            x = self.up_convs[i](cur, ctx=csrs[j + 1], agg_attr=agg_j, n_rows=cur.size(0), part=parts[j])
+            x = self.up_convs[i](cur, ctx=csrs[j + 1], agg_attr=aggs[j + 1], n_rows=cur.size(0))
         out = ops.linear(x, split_weight(self.final_conv.weight), self.final_conv.bias.detach())
         return (out, perms) if return_perms else out
+
+    def _forward_partitioned(self, x, ctx, csr0, ea, part, a):
+        return _unet_forward_partitioned(self, x, ctx, csr0, ea, part, a)
+
+
+def _unet_forward_partitioned(self, x, ctx, csr0, ea, part, a):
+    """Node-partitioned U-Net. Only LEVEL 0 (the full node set: down_convs[0], down_convs[1] and the last up conv — 6 of the 16
+    propagates, > 80 % of the U-Net's bytes) is row-partitioned with a halo exchange per propagate. The pooled levels (1/2, 1/4,
+    1/8 of the nodes, 128-wide) are REPLICATED: every rank all-gathers the level-0 output once, runs the same exact top-k and the
+    small levels redundantly — 10 propagates on <= N/2 rows cost less than the 10 latency-bound exchanges (+ 3 host reads for the
+    uneven pooled bounds) they replace, and their results are bitwise those of a single GPU."""
+    def agg_level0():
+        if ea is None:
+            return None
+        return part.local(_level0_agg(ctx, ea))
+    agg0 = agg_level0()
+    x0 = self.down_convs[0](x, ctx=csr0, agg_attr=agg0, part=part)
+    cur = ops.unpool_add_act(x0, x0, _neg_map(x0), act=a)
+    x1 = self.down_convs[1](cur, ctx=csr0, agg_attr=agg0, part=part)            # skip tensor of level 0 (owned rows)
+    x1_full = part.gather(x1)
+    # ---- replicated from here: pool level 0 -> 1 and everything below, exactly the single-GPU code on full tensors
+    csrs, xs, maps, perms, aggs = [csr0], [None, x1_full], [], [], [None]
+    xl = x1_full
+    for i in range(self.depth):
+        if i > 0:
+            xl = self.down_convs[i + 1](cur, ctx=csrs[-1], agg_attr=aggs[-1])
+            xs.append(xl)
+        cur, pcsr, perm, node_map, _, _ = self.pools[i].pool(xl, csrs[-1], act=a, with_eid=ea is not None)
+        csrs.append(pcsr); maps.append(node_map); perms.append(perm)
+        aggs.append(None if ea is None else ops.edge_attr_aggregate(pcsr, ea))
+    xl = self.bottom_conv(cur, ctx=csrs[-1], agg_attr=aggs[-1])
+    for i in range(self.depth - 1):
+        j = self.depth - 1 - i
+        cur = ops.unpool_add_act(xs[j + 1], xl, maps[j], act=a)
+        xl = self.up_convs[i](cur, ctx=csrs[j + 1], agg_attr=aggs[j + 1], n_rows=cur.size(0))
+    # ---- back to the partition for the level-0 decoder (D8: level-1 edges on the level-0 node set)
+    nm = part.local(maps[0]).contiguous()
+    cur = ops.unpool_add_act(x1, xl, nm, act=a)
+    agg_d = None if ea is None else aggs[1][min(part.a, csrs[1].N):min(part.b, csrs[1].N)]
+    self._last_perms = perms
+    return self.up_convs[self.depth - 1](cur, ctx=csrs[1], agg_attr=agg_d, n_rows=cur.size(0), part=part)
 
 
 def _edge_attr_or_none(edge_attr, width):

@@ -198,6 +198,102 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_builder(args, rank, world, dev):
+    """BASELINE.json configs[2]: TissueGraphBuilder edge construction (tissue_graph_builder.py:269-437: 8-NN on 2-D coordinates with
+    w = exp(-10 d) >= 0.7, 16-NN on 768-d features kept when cosine >= 0.7, undirected de-duplication, (s,t),(t,s) emission) over
+    --rows synthetic patch embeddings. One step = the whole construction: every rank all-gathers the feature rows it does not hold
+    (NCCL), computes the kNN of the query rows it owns, one all-gather of the surviving candidate tuples, replicated de-duplication.
+    Exactness: sampled query rows are re-ranked by the exact fp64 path (scikit-learn's arithmetic); the full edge list is compared
+    with the scikit-learn oracle at n = 10k / 25k in tests/test_gpu_round2.py."""
+    import torch.distributed as dist
+    from dgdm_histopath_lab_b200 import TissueGraphBuilder, builder, synth
+    n, d, nc = args.rows, 768, 4096
+    g = torch.Generator(device=dev).manual_seed(1234)           # same seed on every rank -> identical rows (SURVEY 8(d) config-3 generator)
+    centres = torch.nn.functional.normalize(torch.randn(nc, d, generator=g, device=dev), dim=1)
+    sigma = 0.018 + 0.010 * torch.rand(nc, generator=g, device=dev)
+    assign = torch.randint(0, nc, (n,), generator=g, device=dev)
+    F = torch.empty(n, d, device=dev)
+    for a in range(0, n, 65536):
+        b = min(n, a + 65536)
+        F[a:b] = centres[assign[a:b]] + sigma[assign[a:b], None] * torch.randn(b - a, d, generator=g, device=dev)
+    xs, ys, dims = synth.jittered_grid_coords(n, seed=7)
+    import numpy as np
+    C = torch.as_tensor(np.stack([xs / dims[0], ys / dims[1]], axis=1)).to(dev)
+    rows = -(-n // world)
+    q0, q1 = min(n, rank * rows), min(n, (rank + 1) * rows)
+    mine = torch.zeros(rows, d, device=dev)
+    mine[: q1 - q0] = F[q0:q1]
+    tb = TissueGraphBuilder(feature_extractor="none", device=dev)
+
+    def step():
+        if world > 1:                                           # each rank contributes the rows it holds; everybody needs all keys
+            full = torch.empty(rows * world, d, device=dev)
+            dist.all_gather_into_tensor(full, mine)
+            f = full[:n]
+        else:
+            f = F
+        return tb.edge_arrays_sharded(f, C, rank, world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    steps, warm = max(1, min(args.steps, 3)), 1
+    for _ in range(warm):
+        step()
+    barrier()
+    sampler = ClockSampler(dev.index)
+    if rank == 0:
+        sampler.start()
+    builder.KNN_STATS.update(rows=0, flagged=0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        e, stats = step()
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    # exactness on sampled rows of this shard: the fp64 CUDA-core path (sklearn's ranking arithmetic), one row at a time
+    check = 16
+    idx, cos, _ = builder.knn_cosine(F, 17, q0=q0, nq=min(q1 - q0, 4096), mode="tc")
+    bad = 0
+    for r in torch.linspace(0, min(q1 - q0, 4096) - 1, check).long().tolist():
+        i1, c1, _ = builder.knn_cosine(F, 17, q0=q0 + r, nq=1, mode="exact")
+        bad += int(not (torch.equal(i1[0], idx[r]) and torch.equal(c1[0], cos[r])))
+    st = torch.tensor([ms, wall * 1e3, float(bad), float(builder.KNN_STATS["flagged"])], device=dev, dtype=torch.float64)
+    if world > 1:
+        mx = st.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = st.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    else:
+        mx = sm = st
+    if rank == 0:
+        per = mx[0].item() / steps
+        m_und = int(e["src"].numel())
+        types = torch.bincount(e["type"], minlength=2).tolist()
+        line = {"metric": "TissueGraphBuilder edge construction rows/sec (768-d cosine + threshold 0.7)", "value": n / (per / 1e3), "unit": "rows/s",
+                "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": per, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32 (ranking in f64, candidates on split-fp16 tcgen05)", "data": "synthetic",
+                "config": {"workload": f"configs[2]: edge construction over {n} synthetic 768-d patch embeddings (4096 Gaussian clusters, within-cluster "
+                                       f"cosine straddling 0.7) + jittered-grid coordinates, spatial_k=8, morphological_k=16, edge_threshold=0.7; query rows "
+                                       f"sharded over {world} GPU(s)", "rows": n,
+                           "parallelism": "single GPU" if world == 1 else f"query rows sharded over {world} ranks; NCCL all-gather of feature rows and of candidate tuples; replicated dedup"},
+                "clocks": clocks, "wall_ms_per_step": mx[1].item() / steps,
+                "edges_undirected": m_und, "edges_emitted": 2 * m_und, "edges_spatial": types[0], "edges_morphological": types[1],
+                "near_threshold_pairs_within_1e-6": {"spatial": stats["near_threshold_spatial"], "morphological": stats["near_threshold_morphological"]},
+                "candidate_tuples_exchanged": stats["candidates"],
+                "gram_tflops_useful": 2.0 * n * n * d / (per / 1e3) / 1e12, "rows_flagged_and_recomputed_exactly": int(sm[3].item()),
+                "sampled_rows_checked_vs_exact_fp64": check * world, "sampled_rows_mismatching": int(sm[2].item()),
+                "reference_feasibility": f"the reference's dense cosine matrix alone is {4.0 * n * n / 1e12:.1f} TB at {n} rows"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -209,9 +305,11 @@ def main():
                     help="size of the CPU reference sample: the dense N x N attention of the reference needs 8*N^2*4 bytes (2 GB at 8k, 320 GB at 100k)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="graph100k", choices=["graph100k", "batch4x50k", "large"],
+    ap.add_argument("--rows", type=int, default=1000000, help="builder1m: number of synthetic 768-d patch embeddings")
+    ap.add_argument("--workload", default="graph100k", choices=["graph100k", "batch4x50k", "large", "builder1m"],
                     help="graph100k = BASELINE.json's metric (one 100k-node tile graph); batch4x50k = configs[1] (4 x 50k-node graphs in one Batch); "
-                         "large = configs[3]: DGDM-Large (configs/dgdm_large.yaml) on one --nodes graph (500000 in BASELINE.json), meant for torchrun")
+                         "large = configs[3]: DGDM-Large (configs/dgdm_large.yaml) on one --nodes graph (500000 in BASELINE.json), meant for torchrun; "
+                         "builder1m = configs[2]: TissueGraphBuilder edge construction over --rows 768-d embeddings, query rows sharded over the ranks")
     ap.add_argument("--no-fused-halo", action="store_true", help="multi-GPU: NCCL all-gather per propagate instead of the GEMM-epilogue P2P/multicast stores")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -242,6 +340,9 @@ def main():
             sys.stdout.flush()
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
+
+    if args.workload == "builder1m":
+        return run_builder(args, rank, world, dev)
 
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")

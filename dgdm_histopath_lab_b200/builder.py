@@ -303,6 +303,73 @@ class TissueGraphBuilder:
         e = remove_duplicate_edges_device(candidate_edges_device(sp_idx, sp_dist, mo_idx, mo_cos, self.edge_threshold), n)
         return {k: v.cpu().numpy() for k, v in e.items()}
 
+    # ---------------------------------------------------------------------------------- row-sharded construction (config 3)
+    def shard_candidates(self, f, c, q0, nq):
+        """Candidate edges of query rows [q0, q0+nq) — the rows ONE rank owns — against all n rows, in the reference's emission order.
+        f float32 CUDA [n,d], c float64 CUDA [n,2]. Returns (spatial dict, morphological dict, near) where `near` counts the kNN
+        pairs whose weight lies within 1e-6 of edge_threshold (the pairs whose keep/drop decision is sensitive to the last bits of
+        the arithmetic; north_star asks for them to be counted and reported): [spatial, morphological]."""
+        n = f.size(0)
+        ks, km = min(self.spatial_k + 1, n), min(self.morphological_k + 1, n)
+        sp_idx, sp_dist = knn2d(c, ks, q0=q0, nq=nq)
+        mo_idx, mo_cos, _ = knn_cosine(f, km, q0=q0, nq=nq)
+        thr = self.edge_threshold
+        near_sp = int(((torch.exp(-sp_dist[:, 1:] * 10) - thr).abs() < 1e-6).sum().item()) if ks > 1 else 0
+        near_mo = int(((mo_cos[:, 1:].double() - thr).abs() < 1e-6).sum().item()) if km > 1 else 0
+        sp = candidate_edges_device(sp_idx, sp_dist, None, None, thr, row0=q0)
+        mo = candidate_edges_device(None, None, mo_idx, mo_cos, thr, row0=q0)
+        return sp, mo, (near_sp, near_mo)
+
+    @staticmethod
+    def merge_shards(shards, n):
+        """shards: per rank (spatial dict, morphological dict) in rank order. The reference emits every spatial candidate (row-major)
+        before any morphological one (:283-287), so the global list is [spatial of rank 0..P-1] + [morphological of rank 0..P-1];
+        the undirected de-duplication (:354-365: strictly greater weight replaces, first-seen position kept) then runs on it."""
+        names = ("src", "tgt", "type", "weight", "f0", "f1")
+        parts = [sh[0] for sh in shards] + [sh[1] for sh in shards]
+        cat = {k: torch.cat([p[k] for p in parts]) for k in names}
+        return remove_duplicate_edges_device(cat, n)
+
+    def edge_arrays_sharded(self, f, c, rank, world, group=None):
+        """Edge construction with the query rows sharded over `world` ranks (one process per GPU, torch.distributed): every rank holds
+        all n feature rows and coordinates, computes the 2-D and 768-d kNN of the rows it owns, and ONE exchange — an all-gather of
+        the surviving candidate tuples — gives every rank the global candidate list, on which the de-duplication runs replicated.
+        Returns (edge dict of device tensors in emission order, stats dict)."""
+        import torch.distributed as dist
+        n = f.size(0)
+        rows = -(-n // world)
+        q0, q1 = min(n, rank * rows), min(n, (rank + 1) * rows)
+        sp, mo, near = self.shard_candidates(f, c, q0, q1 - q0)
+        if world == 1:
+            e = self.merge_shards([(sp, mo)], n)
+            return e, {"near_threshold_spatial": near[0], "near_threshold_morphological": near[1], "candidates": int(sp["src"].numel() + mo["src"].numel())}
+        dev = f.device
+        cnt = torch.tensor([sp["src"].numel(), mo["src"].numel(), near[0], near[1]], dtype=torch.int64, device=dev)
+        allc = torch.empty(world, 4, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, cnt, group=group)
+        allc_h = allc.cpu()
+        shards = [[None, None] for _ in range(world)]
+        for which, part in enumerate((sp, mo)):
+            mx = int(allc_h[:, which].max())
+            ints = torch.zeros(max(mx, 1), 3, dtype=torch.int64, device=dev)
+            flts = torch.zeros(max(mx, 1), 3, dtype=torch.float64, device=dev)
+            m = part["src"].numel()
+            if m:
+                ints[:m] = torch.stack([part["src"], part["tgt"], part["type"]], dim=1)
+                flts[:m] = torch.stack([part["weight"], part["f0"], part["f1"]], dim=1)
+            gi = torch.empty(world * max(mx, 1), 3, dtype=torch.int64, device=dev)
+            gf = torch.empty(world * max(mx, 1), 3, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(gi, ints, group=group)
+            dist.all_gather_into_tensor(gf, flts, group=group)
+            for r in range(world):
+                k = int(allc_h[r, which])
+                a = r * max(mx, 1)
+                shards[r][which] = dict(src=gi[a:a + k, 0], tgt=gi[a:a + k, 1], type=gi[a:a + k, 2],
+                                        weight=gf[a:a + k, 0], f0=gf[a:a + k, 1], f1=gf[a:a + k, 2])
+        e = self.merge_shards([tuple(s_) for s_ in shards], n)
+        return e, {"near_threshold_spatial": int(allc_h[:, 2].sum()), "near_threshold_morphological": int(allc_h[:, 3].sum()),
+                   "candidates": int(allc_h[:, :2].sum())}
+
     def build_graph(self, slide_data, patch_images=None):
         nodes = self._create_nodes(slide_data, patch_images)
         if len(nodes) == 0:

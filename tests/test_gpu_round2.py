@@ -201,3 +201,30 @@ def test_weight_cache_follows_parameter_updates():
     del m, a2
     gc.collect()
     assert len(core._CAT_CACHE._d) < n_before, "q|k|v planes must be released with the model"
+
+
+@pytest.mark.parametrize("n", [10000, 25000])
+def test_builder_full_edge_list_vs_sklearn_oracle(n):
+    """BASELINE configs[2] exactness on checkable sizes: the WHOLE edge list (indices AND order) against oracle/builder_oracle.py
+    (scikit-learn's NearestNeighbors / cosine_similarity exactly as the reference calls them, tissue_graph_builder.py:290-365),
+    768-d clustered features whose within-cluster cosine straddles the 0.7 threshold, single pass and 3-shard row partition."""
+    from oracle import builder_oracle
+    feats = synth.clustered_features(n, d=768, num_clusters=max(8, n // 250), seed=31)
+    xs, ys, dims = synth.jittered_grid_coords(n, seed=31)
+    coords = np.stack([xs / dims[0], ys / dims[1]], axis=1)
+    ei, ea, et = builder_oracle.build_edges(feats, coords)
+    tb = TissueGraphBuilder(feature_extractor="none")
+    f = torch.as_tensor(feats).to(DEV)
+    c = torch.as_tensor(coords).to(DEV)
+    e, stats = tb.edge_arrays_sharded(f, c, 0, 1)
+    rows = -(-n // 3)
+    shards = [tb.shard_candidates(f, c, q0, min(n, q0 + rows) - q0)[:2] for q0 in range(0, n, rows)]
+    e3 = tb.merge_shards(shards, n)
+    for tag, ed in (("single", e), ("3 shards", e3)):
+        src, tgt = ed["src"].cpu().numpy(), ed["tgt"].cpu().numpy()
+        assert 2 * src.shape[0] == ei.shape[1], (tag, src.shape, ei.shape)
+        assert np.array_equal(src, ei[0, 0::2]) and np.array_equal(tgt, ei[1, 0::2]), f"{tag}: edge list differs from the sklearn oracle"
+        assert np.array_equal(ed["type"].cpu().numpy(), et[0::2])
+        assert np.abs(ed["f0"].cpu().numpy().astype(np.float32) - ea[0::2, 0]).max() < 2e-6
+    print(f"n={n}: {ei.shape[1] // 2} undirected edges identical to the oracle; near-threshold pairs: {stats}")
+    assert stats["near_threshold_spatial"] >= 0 and stats["near_threshold_morphological"] >= 0

@@ -220,11 +220,29 @@ def test_builder_full_edge_list_vs_sklearn_oracle(n):
     rows = -(-n // 3)
     shards = [tb.shard_candidates(f, c, q0, min(n, q0 + rows) - q0)[:2] for q0 in range(0, n, rows)]
     e3 = tb.merge_shards(shards, n)
+    thr = 0.7
+    ref_pairs = list(zip(ei[0, 0::2].tolist(), ei[1, 0::2].tolist()))
+    ref_w = {pq: float(w) for pq, w in zip(ref_pairs, ea[0::2, 0])}
     for tag, ed in (("single", e), ("3 shards", e3)):
         src, tgt = ed["src"].cpu().numpy(), ed["tgt"].cpu().numpy()
-        assert 2 * src.shape[0] == ei.shape[1], (tag, src.shape, ei.shape)
-        assert np.array_equal(src, ei[0, 0::2]) and np.array_equal(tgt, ei[1, 0::2]), f"{tag}: edge list differs from the sklearn oracle"
-        assert np.array_equal(ed["type"].cpu().numpy(), et[0::2])
-        assert np.abs(ed["f0"].cpu().numpy().astype(np.float32) - ea[0::2, 0]).max() < 2e-6
-    print(f"n={n}: {ei.shape[1] // 2} undirected edges identical to the oracle; near-threshold pairs: {stats}")
+        ours = list(zip(src.tolist(), tgt.tolist()))
+        our_w = {pq: float(w) for pq, w in zip(ours, ed["f0"].cpu().numpy())}
+        und = lambda pq: (min(pq), max(pq))
+        so, sr = {und(p) for p in ours}, {und(p) for p in ref_pairs}
+        diff = so ^ sr
+        # the only admissible differences are pairs whose weight sits within 1e-6 of the threshold: scikit-learn's cosine is an fp32 sgemm
+        # of normalised rows, ours an fp64-accumulated dot rounded once, so a pair at 0.7 +- 1e-7 can land on either side (north_star:
+        # "pairs within 1e-6 of edge_threshold counted and reported")
+        for pq in diff:
+            w = [d_[k] for d_ in (our_w, ref_w) for k in (pq, pq[::-1]) if k in d_]
+            assert w and all(abs(x - thr) < 2e-6 or abs(np.exp(-10 * x) - thr) < 2e-6 for x in w), (tag, pq, w)
+        assert len(diff) <= stats["near_threshold_spatial"] + stats["near_threshold_morphological"], (tag, len(diff), stats)
+        keep_o = [p for p in ours if und(p) not in diff]
+        keep_r = [p for p in ref_pairs if und(p) not in diff]
+        assert keep_o == keep_r, f"{tag}: edge list (indices and order) differs from the sklearn oracle beyond the near-threshold pairs"
+        ty = dict(zip(ours, ed["type"].cpu().numpy().tolist()))
+        assert all(ty[p] == t for p, t in zip(ref_pairs, et[0::2].tolist()) if und(p) not in diff)
+        assert all(abs(our_w[p] - ref_w[p]) < 2e-6 for p in keep_r)
+    ndiff = len(diff)
+    print(f"n={n}: {ei.shape[1] // 2} undirected edges, identical to the oracle up to {ndiff} near-threshold pair(s); counted: {stats}")
     assert stats["near_threshold_spatial"] >= 0 and stats["near_threshold_morphological"] >= 0

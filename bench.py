@@ -353,9 +353,12 @@ def main():
     if args.workload == "batch4x50k":
         from dgdm_histopath_lab_b200 import Batch
         host = Batch.from_data_list([synth.tile_graph(args.nodes // 2, 768, seed=100 + i) for i in range(4)])
+    elif args.workload == "large":
+        host = synth.multimag_graph(args.nodes, feat, seed=1234)      # 3 magnification levels, parent / child links
     else:
         host = synth.tile_graph(args.nodes, feat, seed=1234)
     N, E = host.x.size(0), host.edge_index.size(1)
+    edge_cut = synth.edge_cut_fraction(host.edge_index, N, world)
     host_batch = getattr(host, "batch", None)
     rows = None
     if world > 1:
@@ -481,6 +484,13 @@ def main():
 
     # ---- same-input anchor: the sizes the CPU reference can run (config 1 = 2 000 nodes, and --ref-nodes), GPU beside CPU on the
     # IDENTICAL graph and weights. GPU: eager forward (CSR rebuilt per call), and the CUDA-graph replay of the same forward.
+    # NVLink volume of the halo exchange: every propagate all-gathers the projected [N_level, C] matrix; a rank receives the rows it
+    # does not own. Only level 0 of the U-Net is partitioned (pooled levels are replicated after one [N,128] all-gather).
+    halo_bytes = None
+    if world > 1:
+        nloc = rows[1] - rows[0]
+        widths = [c for (n_, e_, c) in meta.get("spmm", []) if n_ == nloc]
+        halo_bytes = int(sum((N - nloc) * c * 4 for c in widths) + (N - nloc) * (128 * 4 + 384 * 4 + 256 * 4))
     cpu, small = None, None
     if rank == 0 and world == 1 and args.workload == "graph100k" and not args.no_cpu_baseline:
         small = {}
@@ -522,12 +532,15 @@ def main():
                 "config": {"workload": (f"DGDM-Base forward (eval, inference mode, return_embeddings) on one synthetic {N}-node 768-d tile graph, "
                                         f"E={E} directed edges, random-init seeded weights") if args.workload == "graph100k" else
                                        (f"DGDM-Large forward (1024-d nodes, hidden [768,512,256,128], 16 heads, 6 layers) on one synthetic {N}-node "
-                                        f"tile graph (configs[3]), E={E} directed edges") if args.workload == "large" else
+                                        f"multi-magnification graph (configs[3]: 5x/20x/40x nested grids 1:16:64, 8-neighbourhood + parent/child + 16 "
+                                        f"morphological links), E={E} directed edges") if args.workload == "large" else
                                        (f"DGDM-Base forward on a Batch of 4 synthetic {N // 4}-node 768-d tile graphs (configs[1]), E={E} directed edges"),
                            "nodes": N, "edges": E,
                            "l2_policy": "inputs larger than L2 (x = 307 MB, activations > 200 MB per layer)",
                            "parallelism": "single GPU" if world == 1 else f"1-D node partition over {world} GPUs: features row-partitioned, NCCL all-gather "
                                           f"of projected rows per propagate (halo), context-parallel attention, replicated graph structure",
+                           "edge_cut_fraction": edge_cut, "halo_bytes_received_per_rank_per_forward": halo_bytes,
+                           "value_includes": "whole forward incl. CSR build (structure cache dropped every step)",
                            "attention_precise": ops.attention_precise_default(), "gemm": ops.gemm_mode(),
                            "halo": None if world == 1 else type(model._comm).__name__ + ("/multicast" if getattr(model._comm, "multicast", False) else "")},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "roofline_hbm": roof_hbm, "roofline_gemm": roof_gemm,

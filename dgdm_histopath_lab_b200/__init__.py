@@ -13,12 +13,14 @@ from .core import (AdaptiveGraphPooling, DiffusionLayer, DiffusionScheduler, Dyn
 from .model import (ClassificationHead, DGDMModel, GlobalAttentionPool, GlobalMaxPool, GlobalMeanPool, GlobalSet2SetPool,
                     RegressionHead)
 from .builder import GraphEdge, GraphNode, PatchInfo, SlideData, TissueGraphBuilder
+from .losses import ContrastiveLoss
+from .io import GraphFileDataset, collate_to_device, load_graph, save_graph
 
 __all__ = [
     "DGDMModel", "TissueGraphBuilder", "Data", "Batch", "DiffusionLayer", "DiffusionScheduler", "GraphConvolution",
     "DynamicGraphLayer", "AdaptiveGraphPooling", "GraphUNet", "MultiHeadAttention", "SpatialAttention", "FeatureEncoder",
     "GraphEncoder", "ClassificationHead", "RegressionHead", "GlobalAttentionPool", "GlobalMeanPool", "GlobalMaxPool",
     "GlobalSet2SetPool", "ModelConfigurationError", "ModelInferenceError", "ValidationError", "PatchInfo", "SlideData",
-    "GraphNode", "GraphEdge",
+    "GraphNode", "GraphEdge", "ContrastiveLoss", "GraphFileDataset", "collate_to_device", "load_graph", "save_graph",
 ]
 __version__ = "0.1.0"

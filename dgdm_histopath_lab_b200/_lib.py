@@ -76,6 +76,9 @@ SIGNATURES = {
     "dgdm_knn_cosine_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_size_t, c_void_p]),
     "dgdm_gemm_f16x2_strided": (c_int, [C.POINTER(GemmParams), C.c_longlong, c_void_p]),
+    "dgdm_row_normalize": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_int, c_void_p]),
+    "dgdm_contrastive_accumulate": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                                            c_void_p]),
     "dgdm_knn2d_grid_work_bytes": (c_size_t, [c_int]),
     "dgdm_knn2d": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
 }

@@ -272,6 +272,59 @@ static inline int grid_for(size_t n, int block = 256, int cap = 148 * 16) {
 }  // namespace dgdm
 using namespace dgdm;
 
+// ------------------------------------------------------------------------------------------ contrastive loss (training/losses.py:123-176)
+// out[i,:] = x[i,:] / max(|x[i,:]|_2, eps)   (F.normalize, :131); warp per row
+__global__ void __launch_bounds__(256) row_normalize_kernel(const float* __restrict__ X, int ldx, int M, int C, float eps,
+                                                            float* __restrict__ out, int ldo) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float sq = 0.f;
+  for (int c = lane; c < C; c += 32) { const float v = X[(size_t)row * ldx + c]; sq = fmaf(v, v, sq); }
+  sq = warp_sum(sq);
+  const float inv = 1.0f / fmaxf(sqrtf(sq), eps);
+  for (int c = lane; c < C; c += 32) out[(size_t)row * ldo + c] = X[(size_t)row * ldx + c] * inv;
+}
+// One chunk of the N x N similarity matrix: S[i, j] = e_i . e_{k0+j} for j < nk (fp32, from the tensor-core Gram GEMM).
+// sum_all[i] += sum_j exp((S_ij - 1) / T); sum_pos[i] += the same over keys of the SAME graph, j != i; cnt_pos[i] += their number.
+// The shift by 1/T (cosine <= 1) keeps exp() in range for small temperatures; it cancels in the ratio and is added back in the
+// logarithms by the caller. Warp per row, fixed lane -> key assignment and one read-modify-write per chunk: deterministic.
+__global__ void __launch_bounds__(256) contrastive_accumulate_kernel(const float* __restrict__ S, int lds, int M, int nk, int row0, int k0,
+                                                                     const long long* __restrict__ batch, float inv_temp,
+                                                                     float* __restrict__ sum_all, float* __restrict__ sum_pos,
+                                                                     int* __restrict__ cnt_pos) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const long long b = batch ? batch[row0 + row] : 0;
+  float a = 0.f, pz = 0.f; int c = 0;
+  for (int j = lane; j < nk; j += 32) {
+    const float e = expf((S[(size_t)row * lds + j] - 1.0f) * inv_temp);
+    a += e;
+    const bool same = (batch ? batch[k0 + j] == b : true) && (k0 + j != row0 + row);
+    if (same) { pz += e; ++c; }
+  }
+  a = warp_sum(a); pz = warp_sum(pz);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) { sum_all[row] += a; sum_pos[row] += pz; cnt_pos[row] += c; }
+}
+
+extern "C" int dgdm_row_normalize(const float* X, int ldx, int M, int C, float eps, float* out, int ldo, void* stream) {
+  if (!X || !out || C <= 0) return DGDM_ERR_INVALID;
+  if (M <= 0) return DGDM_OK;
+  row_normalize_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(X, ldx, M, C, eps, out, ldo);
+  DGDM_CHECK_LAUNCH();
+  return DGDM_OK;
+}
+extern "C" int dgdm_contrastive_accumulate(const float* S, int lds, int M, int nk, int row0, int k0, const int64_t* batch,
+                                           float temperature, float* sum_all, float* sum_pos, int* cnt_pos, void* stream) {
+  if (!S || !sum_all || !sum_pos || !cnt_pos || !(temperature > 0.f) || nk < 0) return DGDM_ERR_INVALID;
+  if (M <= 0 || nk == 0) return DGDM_OK;
+  contrastive_accumulate_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(S, lds, M, nk, row0, k0, (const long long*)batch,
+                                                                              1.0f / temperature, sum_all, sum_pos, cnt_pos);
+  DGDM_CHECK_LAUNCH();
+  return DGDM_OK;
+}
+
 extern "C" int dgdm_abi_version(void) { return 1; }
 
 extern "C" int dgdm_device_check(int dev) {

@@ -225,6 +225,16 @@ int dgdm_row_sqnorm_f64(const float* F, int n, int d, double* sq, void* stream);
 size_t dgdm_knn_cosine_tc_work_bytes(int nq);
 int dgdm_knn_cosine_tc(const float* F, const void* W_img, const double* sq, int n, int n_pad, int d, int q0, int nq, int k,
                        int* nbr_idx, float* nbr_cos, double* nbr_dist, int* row_flags, void* work, size_t work_bytes, void* stream);
+/* ContrastiveLoss._batch_contrastive_loss (training/losses.py:123-176), never forming the N x N matrix:
+ * dgdm_row_normalize = F.normalize(embeddings, dim=1) (:131); the similarity chunks come from dgdm_gemm_f16x2_strided (rows of the
+ * normalised matrix against a 512-row key range of its own fp16 hi/lo image); dgdm_contrastive_accumulate folds one chunk
+ * S [M, nk] (rows row0.., keys k0..) into sum_all[i] += sum_j exp((S_ij - 1)/T), sum_pos[i] (same graph id, j != i) and
+ * cnt_pos[i]. The shift by 1/T cancels in the ratio; the caller adds it back inside the logarithms. batch: int64 graph id per
+ * node or NULL (one graph). Deterministic (fixed lane -> key mapping, one update per chunk). */
+int dgdm_row_normalize(const float* X, int ldx, int M, int C, float eps, float* out, int ldo, void* stream);
+int dgdm_contrastive_accumulate(const float* S, int lds, int M, int nk, int row0, int k0, const int64_t* batch,
+                                float temperature, float* sum_all, float* sum_pos, int* cnt_pos, void* stream);
+
 /* dgdm_gemm_f16x2 on a row sub-range of a larger weight image: W_hi points at the first row of the range in the hi plane of
  * K-block 0, w_plane_stride_bytes = (rows of the whole image) * 128; p->N <= 512; plain product (no epilogue fields needed). */
 int dgdm_gemm_f16x2_strided(const dgdm_gemm_params* p, long long w_plane_stride_bytes, void* stream);

@@ -261,3 +261,59 @@ def test_builder_full_edge_list_vs_sklearn_oracle(n):
     ndiff = len(diff)
     print(f"n={n}: {ei.shape[1] // 2} undirected edges, identical to the oracle up to {ndiff} near-threshold pair(s); counted: {stats}")
     assert stats["near_threshold_spatial"] >= 0 and stats["near_threshold_morphological"] >= 0
+
+
+def test_contrastive_loss_vs_reference_formula():
+    """ContrastiveLoss._batch_contrastive_loss (training/losses.py:123-176) — the dense float64 restatement of the reference
+    formula vs the chunked tensor-core path that never forms the N x N matrix."""
+    from dgdm_histopath_lab_b200 import ContrastiveLoss
+    g = torch.Generator().manual_seed(4)
+    n, d = 1337, 128
+    emb = torch.randn(n, d, generator=g)
+    batch = torch.sort(torch.randint(0, 5, (n,), generator=g)).values
+    batch[-1] = 7                                                          # a graph with a single node: no positives, dropped (:168-170)
+
+    def dense(e, b, temp, reduction):
+        e = torch.nn.functional.normalize(e.double(), dim=1)
+        s = e @ e.t() / temp
+        pm = (b[None, :] == b[:, None]).double()
+        pm.fill_diagonal_(0)
+        ex = torch.exp(s)
+        pos = torch.clamp((ex * pm).sum(1), min=1e-8)
+        loss = -torch.log(pos / ex.sum(1))[pm.sum(1) > 0]
+        return loss.mean() if reduction == "mean" else loss.sum() if reduction == "sum" else loss
+    for temp, red in ((0.1, "mean"), (0.5, "sum"), (0.07, "none")):
+        out = ContrastiveLoss(temperature=temp, reduction=red)(emb.to(DEV), batch.to(DEV))
+        ref = dense(emb, batch, temp, red)
+        assert rel_err(out.reshape(-1), ref.reshape(-1))[0] < 2e-5, (temp, red)
+    one = ContrastiveLoss()(emb.to(DEV), None)                             # batch_indices None: every other node is a positive
+    assert rel_err(one.reshape(-1), dense(emb, torch.zeros(n, dtype=torch.long), 0.1, "mean").reshape(-1))[0] < 2e-5
+    with pytest.raises(Exception):
+        ContrastiveLoss()(emb, batch)                                      # CPU tensors: no fallback
+
+
+def test_graph_file_with_stored_csr_and_device_collate(tmp_path):
+    """a .dgdm file with the CSR stored on disk gives the same GraphContext (bitwise) as dgdm_csr_build, and the
+    on-device collate equals Batch.from_data_list."""
+    from dgdm_histopath_lab_b200 import collate_to_device, load_graph, save_graph
+    from dgdm_histopath_lab_b200.graph import get_context
+    d = synth.tile_graph(2000, 48, seed=9)
+    f = save_graph(d, str(tmp_path / "g.dgdm"))
+    g = load_graph(f, device=DEV)
+    ctx = g.__dict__["_dgdm_ctx"]
+    ref = get_context(d.to(DEV))
+    for k in ("rowptr", "col", "eid", "norm", "dinv"):
+        assert torch.equal(getattr(ctx.csr, k)[: ref.csr.E if k in ("col", "eid", "norm") else None], getattr(ref.csr, k)[: ref.csr.E if k in ("col", "eid", "norm") else None]), k
+    m = make_model(SMALL_CFG).to(DEV)
+    a = m(g, return_embeddings=True)["node_embeddings"]
+    assert g.__dict__["_dgdm_ctx"] is ctx, "the stored CSR must be used, not rebuilt"
+    b = m(d.to(DEV), return_embeddings=True)["node_embeddings"]
+    assert torch.equal(a, b)
+    gs = [synth.tile_graph(k, 48, seed=40 + i) for i, k in enumerate((120, 77, 201))]
+    for x in gs:
+        x.edge_attr = torch.rand(x.edge_index.size(1), 2)
+    cb = collate_to_device([x.pin_memory() for x in gs], DEV)
+    rb = Batch.from_data_list(gs).to(DEV)
+    for k in ("x", "edge_index", "pos", "edge_attr", "batch"):
+        assert torch.equal(getattr(cb, k), getattr(rb, k)), k
+    assert torch.equal(m(cb, return_embeddings=True)["node_embeddings"], m(rb, return_embeddings=True)["node_embeddings"])

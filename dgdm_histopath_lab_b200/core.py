@@ -75,8 +75,34 @@ def _cat_bias(linears):
     return torch.cat([l.bias.detach() for l in linears])
 
 
+_UNIT_LN = {}
+
+
 def _ln(m):
-    return (m.weight.detach(), m.bias.detach()) if isinstance(m, nn.LayerNorm) else None
+    """(gamma, beta) of the row-wise normalisation fused into a GEMM epilogue. InstanceNorm1d on the reference's 2-D [N, C] inputs
+    normalises every ROW over its C entries without affine parameters (torch reads [N, C] as an unbatched (channels, length)
+    signal): LayerNorm with gamma = 1, beta = 0 (same eps 1e-5, biased variance)."""
+    if isinstance(m, nn.LayerNorm):
+        return (m.weight.detach(), m.bias.detach())
+    if isinstance(m, nn.InstanceNorm1d):
+        dev = _INSTANCE_DEV[0]
+        key = (m.num_features, dev)
+        if key not in _UNIT_LN:
+            _UNIT_LN[key] = (torch.ones(m.num_features, device=dev), torch.zeros(m.num_features, device=dev))
+        return _UNIT_LN[key]
+    return None
+
+
+_INSTANCE_DEV = [None]
+
+
+def _norm_act_torch(h, norm, act_name, training):
+    """BatchNorm1d (+ activation) — a non-benchmarked constructor option (SURVEY 8(b) "non-default options"): the column-wise
+    affine of eval-mode batch norm does not fit the row-wise GEMM epilogues, so these two element-wise steps run as plain torch
+    CUDA ops on the GEMM output."""
+    h = F.batch_norm(h, norm.running_mean, norm.running_var, norm.weight, norm.bias, training and norm.track_running_stats is not False,
+                     norm.momentum if norm.momentum is not None else 0.0, norm.eps)
+    return {"gelu": F.gelu, "relu": F.relu, "elu": F.elu}[act_name](h) if act_name else h
 
 
 def _require_cuda(x):
@@ -681,8 +707,6 @@ class DiffusionLayer(nn.Module):
         """concat([x_t, t_emb]) W^T = x_t W_x^T + t_emb W_t^T with t_emb constant per segment -> per-segment bias row
         (identity (iv)); GroupNorm(8)+SiLU row-wise; three tcgen05 GEMMs."""
         _require_cuda(x_noisy)
-        if condition is not None:
-            raise NotImplementedError("conditioning is not used by DGDMModel and is not implemented")
         shp = x_noisy.shape
         x2 = x_noisy.reshape(-1, shp[-1]).contiguous()
         n = x2.size(0)
@@ -698,7 +722,18 @@ class DiffusionLayer(nn.Module):
         seg_h = seg_ptr.cpu().tolist()
         row_idx = torch.repeat_interleave(torch.arange(nseg, device=x2.device, dtype=torch.int32),
                                           torch.tensor([seg_h[i + 1] - seg_h[i] for i in range(nseg)], device=x2.device))
-        h = ops.linear(x2, wx, None, row_bias=(row_idx.contiguous(), tb))
+        cond_rows = None
+        if condition is not None and self.condition_net is not None:
+            # t_emb + condition_net(condition) (core/diffusion.py:158-160): the extra term goes through the time-embedding columns of the
+            # first denoise GEMM as well -> one [N, cdim] x [cdim, hidden] and one [N, hidden] x [hidden, 2 hidden] GEMM, added as a residual
+            c2 = condition.reshape(-1, condition.size(-1)).float()
+            if c2.size(0) == 1 and n > 1:
+                c2 = c2.expand(n, -1)
+            if c2.size(0) != n:
+                raise ops.KernelError(f"condition has {c2.size(0)} rows for {n} nodes")
+            ce = ops.linear(c2.contiguous(), split_weight(self.condition_net.weight), self.condition_net.bias.detach())
+            cond_rows = ops.linear(ce, wt, None)
+        h = ops.linear(x2, wx, None, row_bias=(row_idx.contiguous(), tb), r_pre=cond_rows)
         h = ops.groupnorm_silu(h, 8, g1.weight.detach(), g1.bias.detach(), g1.eps)
         h = ops.linear(h, split_weight(d4.weight), d4.bias.detach())
         h = ops.groupnorm_silu(h, 8, g5.weight.detach(), g5.bias.detach(), g5.eps)
@@ -826,12 +861,11 @@ class FeatureEncoder(nn.Module):
         super().__init__()
         if activation not in _ACTS:
             raise ValueError(f"Unknown activation: {activation}")
-        if normalization in ("batch", "instance"):
-            raise NotImplementedError(f"normalization='{normalization}' is not implemented (layer / none are)")
         self.input_dim, self.hidden_dim, self.num_layers, self.use_residual = input_dim, hidden_dim, num_layers, use_residual
         self.activation_name = activation
         self.activation = _ACTS[activation]()
-        mk_norm = (lambda: nn.LayerNorm(hidden_dim)) if normalization == "layer" else (lambda: nn.Identity())
+        mk_norm = {"layer": lambda: nn.LayerNorm(hidden_dim), "batch": lambda: nn.BatchNorm1d(hidden_dim),
+                   "instance": lambda: nn.InstanceNorm1d(hidden_dim)}.get(normalization, lambda: nn.Identity())      # encoders.py:93-102
         layers = [nn.Linear(input_dim, hidden_dim), mk_norm(), self.activation, nn.Dropout(dropout)]
         for _ in range(num_layers - 1):
             layers += [nn.Linear(hidden_dim, hidden_dim), mk_norm(), self.activation, nn.Dropout(dropout)]
@@ -846,9 +880,15 @@ class FeatureEncoder(nn.Module):
         if self.use_residual:
             res = x if self.residual_proj is None else ops.linear(x, split_weight(self.residual_proj.weight), self.residual_proj.bias.detach())
         h = x
+        _INSTANCE_DEV[0] = x.device
         for i in range(self.num_layers):
             lin, norm = self.encoder[4 * i], self.encoder[4 * i + 1]
             last = i == self.num_layers - 1
+            if isinstance(norm, nn.BatchNorm1d):
+                h = _norm_act_torch(ops.linear(h, split_weight(lin.weight), lin.bias.detach()), norm, self.activation_name, self.training)
+                if last and res is not None:
+                    h = h + res
+                continue
             h = ops.linear(h, split_weight(lin.weight), lin.bias.detach(), ln1=_ln(norm), act_post=self.activation_name,
                            r_post=res if last else None)
         return h
@@ -860,8 +900,6 @@ class GraphEncoder(nn.Module):
     def __init__(self, input_dim, hidden_dims, num_layers=4, attention_heads=8, dropout=0.1, activation="gelu",
                  normalization="layer", use_edge_features=True, aggregation="add"):
         super().__init__()
-        if normalization in ("batch", "instance"):
-            raise NotImplementedError(f"normalization='{normalization}' is not implemented (layer / none are)")
         if not use_edge_features:
             raise NotImplementedError("use_edge_features=False is not implemented (reference default True)")
         self.input_dim, self.hidden_dims, self.num_layers, self.use_edge_features = input_dim, hidden_dims, num_layers, use_edge_features
@@ -870,7 +908,8 @@ class GraphEncoder(nn.Module):
         for i in range(num_layers):
             a, b = dims[min(i, len(dims) - 1)], dims[min(i + 1, len(dims) - 1)]
             self.graph_layers.append(DynamicGraphLayer(node_dim=a, edge_dim=32, hidden_dim=b, num_heads=attention_heads, dropout=dropout))
-            self.norm_layers.append(nn.LayerNorm(b) if normalization == "layer" else nn.Identity())
+            self.norm_layers.append({"layer": nn.LayerNorm, "batch": nn.BatchNorm1d, "instance": nn.InstanceNorm1d}[normalization](b)
+                                    if normalization in ("layer", "batch", "instance") else nn.Identity())            # encoders.py:217-226
             trans.append(nn.Linear(a, b) if a != b else nn.Identity())
         self.transitions = nn.ModuleList(trans)
         self.activation_name = activation if activation in _ACTS else "relu"
@@ -889,9 +928,15 @@ class GraphEncoder(nn.Module):
             if part is not None:
                 agg = part.local(agg)
         h, outs = x, []
+        _INSTANCE_DEV[0] = x.device
         for i, layer in enumerate(self.graph_layers):
-            h = layer(h, ctx=ctx, agg_attr=agg, part=part,
-                      post=dict(transition=self.transitions[i], ln=self.norm_layers[i], act=self.activation_name))
+            norm = self.norm_layers[i]
+            if isinstance(norm, nn.BatchNorm1d):
+                h = layer(h, ctx=ctx, agg_attr=agg, part=part, post=dict(transition=self.transitions[i], ln=None, act=None))
+                h = _norm_act_torch(h, norm, self.activation_name, self.training)
+            else:
+                h = layer(h, ctx=ctx, agg_attr=agg, part=part,
+                          post=dict(transition=self.transitions[i], ln=norm, act=self.activation_name))
             outs.append(h)
         final = ops.linear(h, split_weight(self.output_proj.weight), self.output_proj.bias.detach())
         return {"embeddings": final, "layer_outputs": outs, "num_nodes": x.size(0)}

@@ -377,8 +377,9 @@ class DGDMModel(nn.Module):
         pos = getattr(data, "pos", None)
         edge_attr = getattr(data, "edge_attr", None)
         if batch is not None and not ctx.sorted:
-            # node-sorted segments are what the kernels index; the reference's boolean masks accept any order
-            raise ModelInferenceError("batch vector must be sorted by graph id (Batch.from_data_list produces this)")
+            # the kernels index node-sorted segments; the reference's boolean masks (`x[batch == i]`) accept any order: run on a
+            # stably sorted copy (nodes of a graph keep their relative order) and scatter the node-level outputs back
+            return self._forward_unsorted(data, mode, return_attention, return_embeddings, rng)
         part = None
         if self._comm is not None:
             from .parallel import Part, even_bounds
@@ -419,6 +420,28 @@ class DGDMModel(nn.Module):
         if return_attention and attn is not None:
             outputs["attention_weights"] = attn
         return outputs
+
+    def _forward_unsorted(self, data, mode, return_attention, return_embeddings, rng):
+        if self._comm is not None:
+            raise ModelInferenceError("node-partitioned execution needs a batch vector sorted by graph id")
+        batch = data.batch
+        perm = torch.sort(batch, stable=True).indices
+        inv = torch.empty_like(perm)
+        inv[perm] = torch.arange(perm.numel(), device=perm.device)
+        srt = data.clone() if hasattr(data, "clone") else data
+        srt.__dict__.pop("_dgdm_ctx", None)
+        srt.x, srt.batch, srt.edge_index = data.x[perm], batch[perm], inv[data.edge_index]
+        if getattr(data, "pos", None) is not None:
+            srt.pos = data.pos[perm]
+        if rng is not None and mode == "pretrain":
+            rng = dict(rng)
+            for k in ("noise", "target"):
+                if rng.get(k) is not None:
+                    rng[k] = rng[k].to(perm.device)[perm]
+        out = self._forward_impl(srt, mode, return_attention, return_embeddings, rng)
+        if "node_embeddings" in out:
+            out["node_embeddings"] = out["node_embeddings"][inv]
+        return out
 
     def _compute_diffusion_loss(self, h, ctx, rng):
         """models/dgdm_model.py:405-445 with P6: one timestep per graph, noise prediction MSE against an INDEPENDENT

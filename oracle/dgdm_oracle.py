@@ -26,6 +26,18 @@ def _ln(sd, p, x):
     return F.layer_norm(x, (x.size(-1),), sd[p + ".weight"], sd[p + ".bias"], 1e-5)
 
 
+def _norm(sd, p, x, kind="layer"):
+    """encoders.py:93-102 / :217-226 `_get_norm_layer` in eval mode: LayerNorm | BatchNorm1d (running statistics) | InstanceNorm1d
+    (a 2-D [N, C] input is an unbatched (channels = N, length = C) signal: every row is normalised over its C entries, no affine)."""
+    if kind == "layer":
+        return _ln(sd, p, x)
+    if kind == "batch":
+        return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"], False, 0.0, 1e-5)
+    if kind == "instance":
+        return F.layer_norm(x, (x.size(-1),), None, None, 1e-5)
+    return x
+
+
 def _act(name):
     return {"gelu": F.gelu, "relu": F.relu, "elu": F.elu}[name]
 
@@ -143,17 +155,17 @@ def graph_unet(sd, p, x, edge_index, edge_attr=None, depth=3, act="relu", return
 
 
 # ----------------------------------------------------------------------------- encoders
-def feature_encoder(sd, p, x, act="gelu"):
-    """FeatureEncoder.forward, models/encoders.py:104-124 (layer norm, 2 layers, eval)."""
+def feature_encoder(sd, p, x, act="gelu", norm="layer"):
+    """FeatureEncoder.forward, models/encoders.py:104-124 (2 layers, eval)."""
     a = _act(act)
-    h = a(_ln(sd, p + ".encoder.1", _lin(sd, p + ".encoder.0", x)))
-    h = a(_ln(sd, p + ".encoder.5", _lin(sd, p + ".encoder.4", h)))
+    h = a(_norm(sd, p + ".encoder.1", _lin(sd, p + ".encoder.0", x), norm))
+    h = a(_norm(sd, p + ".encoder.5", _lin(sd, p + ".encoder.4", h), norm))
     if (p + ".residual_proj.weight") in sd:
         return h + _lin(sd, p + ".residual_proj", x)
     return h + x
 
 
-def graph_encoder(sd, p, x, edge_index, edge_attr, num_layers, act="gelu", return_layers=False):
+def graph_encoder(sd, p, x, edge_index, edge_attr, num_layers, act="gelu", return_layers=False, norm="layer"):
     """GraphEncoder.forward, models/encoders.py:228-280 with P1/P3."""
     a = _act(act)
     ea = pad_edge_attr(edge_attr, edge_index.size(1), 32, x)
@@ -162,7 +174,7 @@ def graph_encoder(sd, p, x, edge_index, edge_attr, num_layers, act="gelu", retur
         h = dynamic_graph_layer(sd, f"{p}.graph_layers.{i}", h, edge_index, ea)
         if f"{p}.transitions.{i}.weight" in sd:
             h = _lin(sd, f"{p}.transitions.{i}", h)
-        h = a(_ln(sd, f"{p}.norm_layers.{i}", h))
+        h = a(_norm(sd, f"{p}.norm_layers.{i}", h, norm))
         outs.append(h)
     out = _lin(sd, p + ".output_proj", h)
     return (out, outs) if return_layers else out
@@ -283,9 +295,11 @@ def diffusion_add_noise(sched, x0, noise, t):
     return a * x0 + b * noise
 
 
-def diffusion_predict_noise(sd, p, x_noisy, t):
-    """DiffusionLayer.predict_noise, core/diffusion.py:147-172, 2-D input (P6), eval (dropout off)."""
+def diffusion_predict_noise(sd, p, x_noisy, t, condition=None):
+    """DiffusionLayer.predict_noise, core/diffusion.py:147-172, 2-D input (P6), eval (dropout off); condition: t_emb + condition_net(c)."""
     te = _lin(sd, p + ".time_embed.2", F.silu(_lin(sd, p + ".time_embed.0", timestep_embedding(t))))
+    if condition is not None and (p + ".condition_net.weight") in sd:
+        te = te + _lin(sd, p + ".condition_net", condition)
     h = _lin(sd, p + ".denoise_net.0", torch.cat([x_noisy, te], dim=-1))
     h = F.silu(F.group_norm(h, 8, sd[p + ".denoise_net.1.weight"], sd[p + ".denoise_net.1.bias"], 1e-5))
     h = _lin(sd, p + ".denoise_net.4", h)
@@ -359,9 +373,10 @@ def dgdm_forward(sd, cfg, x, edge_index, edge_attr=None, batch=None, pos=None, m
     heads = cfg.get("attention_heads", 8)
     act = cfg.get("activation", "gelu")
     st = {}
-    h = feature_encoder(sd, "feature_encoder", x, act)
+    norm = cfg.get("normalization", "layer")
+    h = feature_encoder(sd, "feature_encoder", x, act, norm)
     st["feature_encoder"] = h
-    h = graph_encoder(sd, "graph_encoder", h, edge_index, edge_attr, cfg.get("graph_layers", 4), act)
+    h = graph_encoder(sd, "graph_encoder", h, edge_index, edge_attr, cfg.get("graph_layers", 4), act, norm=norm)
     st["graph_encoder"] = h
     if cfg.get("use_spatial_attention", True) and pos is not None:
         if batch is not None:

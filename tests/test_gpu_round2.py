@@ -347,15 +347,16 @@ def test_diffusion_conditioning_vs_oracle():
 
 
 def test_unsorted_batch_vector_is_accepted():
-    """the reference selects nodes with boolean masks (models/dgdm_model.py:343-350), so `batch` may be in any order"""
-    m = make_model(SMALL_CFG).to(DEV)
+    """the reference selects nodes with boolean masks (models/dgdm_model.py:343-350), so `batch` may be in any order. (The model is
+    NOT permutation-equivariant — D8 applies pooled-graph indices to the un-pooled node set — so the check is against the oracle
+    on the same shuffled input, not against the sorted run.)"""
+    m = make_model(SMALL_CFG)
     b = synth.tile_batch(3, 90, 48, seed=21)
-    ref = m(b.to(DEV), return_embeddings=True)
     perm = torch.randperm(b.x.size(0), generator=torch.Generator().manual_seed(1))
     inv = torch.empty_like(perm); inv[perm] = torch.arange(perm.numel())
     sh = Data(x=b.x[perm], edge_index=inv[b.edge_index], pos=b.pos[perm])
     sh.batch = b.batch[perm]
-    out = m(sh.to(DEV), return_embeddings=True)
-    assert rel_err(out["graph_embedding"], ref["graph_embedding"])[0] < 2e-5
-    # node order inside a graph changes the fp32 summation order of attention / pooling slightly; top-k ties aside the rows match
-    assert rel_err(out["node_embeddings"], ref["node_embeddings"][perm.to(DEV)])[0] < TOL
+    ref = O.dgdm_forward(sd_cpu(m), oracle_cfg(SMALL_CFG), sh.x, sh.edge_index, None, sh.batch, sh.pos)
+    out = m.to(DEV)(sh.to(DEV), return_embeddings=True)
+    assert rel_err(out["graph_embedding"], ref["graph_embedding"])[0] < TOL
+    assert rel_err(out["node_embeddings"], ref["node_embeddings"])[0] < TOL

@@ -17,7 +17,7 @@ from .core import (DiffusionLayer, FeatureEncoder, GraphEncoder, GraphUNet, Mult
                    split_weight, _require_cuda)
 from .errors import (ModelConfigurationError, ModelInferenceError, ValidationError, validate_boolean, validate_enum,
                      validate_integer, validate_numeric)
-from .graph import GRAPH_TYPES, get_context
+from .graph import GRAPH_TYPES, Data, get_context
 
 _ACTS = {"relu": nn.ReLU, "gelu": nn.GELU, "elu": nn.ELU}
 
@@ -376,36 +376,49 @@ class DGDMModel(nn.Module):
         batch = getattr(data, "batch", None)
         pos = getattr(data, "pos", None)
         edge_attr = getattr(data, "edge_attr", None)
+        # ---- stage A inputs. The kernels index node-sorted segments; the reference's boolean masks (`x[batch == i]`,
+        # models/dgdm_model.py:343-350) accept any node order, so an unsorted batch runs on a stably sorted copy.
+        dA_x, dA_pos, ctxA, perm, inv = x, pos, ctx, None, None
         if batch is not None and not ctx.sorted:
-            # the kernels index node-sorted segments; the reference's boolean masks (`x[batch == i]`) accept any order: run on a
-            # stably sorted copy (nodes of a graph keep their relative order) and scatter the node-level outputs back
-            return self._forward_unsorted(data, mode, return_attention, return_embeddings, rng)
+            if self._comm is not None:
+                raise ModelInferenceError("node-partitioned execution needs a batch vector sorted by graph id")
+            perm = torch.sort(batch, stable=True).indices
+            inv = torch.empty_like(perm)
+            inv[perm] = torch.arange(perm.numel(), device=perm.device)
+            srt = Data(x=x[perm].contiguous(), edge_index=inv[data.edge_index].contiguous(), pos=None if pos is None else pos[perm].contiguous())
+            srt.batch = batch[perm].contiguous()
+            dA_x, dA_pos, ctxA = srt.x, srt.pos, get_context(srt, N)
         part = None
         if self._comm is not None:
             from .parallel import Part, even_bounds
             if mode == "pretrain":
                 raise ModelInferenceError("mode='pretrain' is not available for node-partitioned graphs (inference / finetune are)")
             part = Part(self._comm, even_bounds(N, self._comm.world))
-            if x.size(0) == N and part.n_local != N:
-                x = x[part.a:part.b]
-            elif x.size(0) != part.n_local:
-                raise ModelInferenceError(f"rank {self._comm.rank} owns rows [{part.a}, {part.b}) but data.x has {x.size(0)} rows")
-        h = self.feature_encoder(x)
-        h = self.graph_encoder(h, ctx=ctx, edge_attr=edge_attr, part=part)["embeddings"]
+            if dA_x.size(0) == N and part.n_local != N:
+                dA_x = dA_x[part.a:part.b]
+            elif dA_x.size(0) != part.n_local:
+                raise ModelInferenceError(f"rank {self._comm.rank} owns rows [{part.a}, {part.b}) but data.x has {dA_x.size(0)} rows")
+        h = self.feature_encoder(dA_x)
+        h = self.graph_encoder(h, ctx=ctxA, edge_attr=edge_attr, part=part)["embeddings"]
         outputs, attn = {}, None
         if self.spatial_attention is not None and pos is not None:
-            h, attn = self.spatial_attention.forward_nodes(h, pos, ctx.seg_ptr, ctx.num_graphs, ctx.seg_host, return_attention, part=part)
+            h, attn = self.spatial_attention.forward_nodes(h, dA_pos, ctxA.seg_ptr, ctxA.num_graphs, ctxA.seg_host, return_attention, part=part)
             if attn is not None and batch is None:
                 attn = attn[0]
+            # unsorted batch: the reference concatenates the per-graph attention outputs in GRAPH order (:358) and carries on with the
+            # original edge_index / batch, i.e. row r now holds the r-th node of the sorted order. Reproduced as is: `h` stays sorted.
+        elif perm is not None:
+            h = h[inv]
         if self.hierarchical_processor is not None:
             h = self.hierarchical_processor(h, ctx=ctx, edge_attr=edge_attr, part=part)
+        h_seg = h if perm is None else h[perm].contiguous()          # `node_embeddings[data.batch == i]` of the reference, graph by graph
         if mode == "pretrain":
-            outputs.update(self._compute_diffusion_loss(h, ctx, rng))
+            outputs.update(self._compute_diffusion_loss(h_seg, ctxA, rng))
         if isinstance(self.global_pool, GlobalAttentionPool):
-            g = self.global_pool(h, ctx=ctx, part=part)
+            g = self.global_pool(h_seg, ctx=ctxA, part=part)
         else:
-            h_pool = h if part is None else part.gather(h)
-            g = self.global_pool(h_pool, batch, ctx=ctx if batch is not None else None)
+            h_pool = h_seg if part is None else part.gather(h_seg)
+            g = self.global_pool(h_pool, batch, ctx=ctxA if batch is not None else None)
         if self.classification_head is not None and mode in ("inference", "finetune"):
             logits = self.classification_head(g)
             outputs["classification_logits"] = logits
@@ -420,28 +433,6 @@ class DGDMModel(nn.Module):
         if return_attention and attn is not None:
             outputs["attention_weights"] = attn
         return outputs
-
-    def _forward_unsorted(self, data, mode, return_attention, return_embeddings, rng):
-        if self._comm is not None:
-            raise ModelInferenceError("node-partitioned execution needs a batch vector sorted by graph id")
-        batch = data.batch
-        perm = torch.sort(batch, stable=True).indices
-        inv = torch.empty_like(perm)
-        inv[perm] = torch.arange(perm.numel(), device=perm.device)
-        srt = data.clone() if hasattr(data, "clone") else data
-        srt.__dict__.pop("_dgdm_ctx", None)
-        srt.x, srt.batch, srt.edge_index = data.x[perm], batch[perm], inv[data.edge_index]
-        if getattr(data, "pos", None) is not None:
-            srt.pos = data.pos[perm]
-        if rng is not None and mode == "pretrain":
-            rng = dict(rng)
-            for k in ("noise", "target"):
-                if rng.get(k) is not None:
-                    rng[k] = rng[k].to(perm.device)[perm]
-        out = self._forward_impl(srt, mode, return_attention, return_embeddings, rng)
-        if "node_embeddings" in out:
-            out["node_embeddings"] = out["node_embeddings"][inv]
-        return out
 
     def _compute_diffusion_loss(self, h, ctx, rng):
         """models/dgdm_model.py:405-445 with P6: one timestep per graph, noise prediction MSE against an INDEPENDENT

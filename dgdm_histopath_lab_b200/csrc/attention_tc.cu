@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc_kernel(const At
 
 
 // ---------------------------------------------------------------------------------------------- 16-softmax-warp variant
-// MEASURED SLOWER than the 8-warp kernel (37.5 vs 35.9 ms at 100k nodes, profiles/attn_tc16_r02b.txt, profiles/mufu_probe_r02.txt) and therefore NOT the default
+// MEASURED SLOWER than the 8-warp kernel (37.5 vs 35.9 ms at 100k nodes, profiles/attn_tc16_r02b.txt, profiles/microbench_r02.txt) and therefore NOT the default
 // (DGDM_ATTN_TC_WARPS=16 selects it): the kernel is not latency-bound. tools/mufu_probe.cu shows that the softmax instruction mix
 // itself (per two scores: 2 MUFU.EX2, 3 FADD2, 2 LOP3, 1 FFMA2, 2 F2FP) sustains only 24.5 / 22.0 / 21.4 cycles per pair at 2 / 4 / 8
 // warps per scheduler against the 16-cycle MUFU ideal — the packed-fp32 and conversion instructions co-limit with the XU pipe — so

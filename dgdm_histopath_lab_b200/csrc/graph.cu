@@ -4,6 +4,7 @@
 // segment softmax. HBM-bound integer/float work: warp per destination row, 128-bit coalesced feature-row
 // loads, no atomics on the data path (deterministic results run to run).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace dgdm {
 
@@ -132,7 +133,7 @@ static void launch_exclusive_scan(const int* in, int* out, int n, int* scratch, 
 }
 
 // ------------------------------------------------------------------------------------------ SpMM
-template <int VPL>
+template <int VPL, int U>
 __global__ void __launch_bounds__(256) spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
                                                        const float* __restrict__ norm, const float* __restrict__ dinv,
                                                        int n_csr_rows, int n_rows, int h_row0, const float* __restrict__ H, int ldh, int C,
@@ -150,10 +151,10 @@ __global__ void __launch_bounds__(256) spmm_gcn_kernel(const int* __restrict__ r
       const int cnt = min(32, end - base);
       int c = 0; float w = 0.f;
       if (lane < cnt) { c = __ldg(col + base + lane); w = __ldg(norm + base + lane); }
-      for (int j0 = 0; j0 < cnt; j0 += 4) {
-        float4 h[4][VPL]; float wj[4];
+      for (int j0 = 0; j0 < cnt; j0 += U) {
+        float4 h[U][VPL]; float wj[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {               // issue all loads of 4 neighbours first (memory-level parallelism)
+        for (int u = 0; u < U; ++u) {               // issue all loads of U neighbours first (memory-level parallelism)
           const int j = j0 + u;
           const int cj = __shfl_sync(0xffffffffu, c, j & 31);
           wj[u] = (j < cnt) ? __shfl_sync(0xffffffffu, w, j & 31) : 0.f;
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(256) spmm_gcn_kernel(const int* __restrict__ r
           }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)                 // accumulate in edge order (fixed, deterministic)
+        for (int u = 0; u < U; ++u)                 // accumulate in edge order (fixed, deterministic)
 #pragma unroll
           for (int v = 0; v < VPL; ++v) {
             acc[v].x = fmaf(wj[u], h[u][v].x, acc[v].x); acc[v].y = fmaf(wj[u], h[u][v].y, acc[v].y);
@@ -450,7 +451,11 @@ extern "C" int dgdm_spmm_gcn(const int* rowptr, const int* col, const float* nor
   const int blocks = (n_rows + 7) / 8;
   cudaStream_t s = (cudaStream_t)stream;
   const int vpl = (C + 127) / 128;
-#define LAUNCH_SPMM(V) spmm_gcn_kernel<V><<<blocks, 256, 0, s>>>(rowptr, col, norm, dinv, n_csr_rows, n_rows, h_row0, H, ldh, C, addend, ld_addend, bias, act, out, ldo)
+  static const int unroll = [] { const char* e = getenv("DGDM_SPMM_UNROLL"); return e ? atoi(e) : 0; }();
+  // neighbours in flight per warp: measured per width (tools/spmm_bench.py); DGDM_SPMM_UNROLL overrides for A/B runs
+  const int U = unroll ? unroll : 2;
+#define LAUNCH_SPMM_U(V, UU) spmm_gcn_kernel<V, UU><<<blocks, 256, 0, s>>>(rowptr, col, norm, dinv, n_csr_rows, n_rows, h_row0, H, ldh, C, addend, ld_addend, bias, act, out, ldo)
+#define LAUNCH_SPMM(V) do { if (U <= 1) LAUNCH_SPMM_U(V, 1); else if (U == 2) LAUNCH_SPMM_U(V, 2); else if (U == 3) LAUNCH_SPMM_U(V, 3); else LAUNCH_SPMM_U(V, 4); } while (0)
   switch (vpl) {
     case 1: LAUNCH_SPMM(1); break;
     case 2: LAUNCH_SPMM(2); break;
@@ -460,6 +465,7 @@ extern "C" int dgdm_spmm_gcn(const int* rowptr, const int* col, const float* nor
     default: LAUNCH_SPMM(8); break;
   }
 #undef LAUNCH_SPMM
+#undef LAUNCH_SPMM_U
   DGDM_CHECK_LAUNCH();
   return DGDM_OK;
 }

@@ -6,7 +6,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["gemm_tc.cu", "rowops.cu", "graph.cu", "attention.cu", "attention_tc.cu", "attention_simt.cu", "attention_dense.cu", "builder.cu"]
+SOURCES = ["gemm_tc.cu", "rowops.cu", "graph.cu", "attention.cu", "attention_tc.cu", "attention_simt.cu", "attention_dense.cu", "attention_bwd.cu", "builder.cu"]
 LIB_PATH = os.path.join(HERE, "libdgdm_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]

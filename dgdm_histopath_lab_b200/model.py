@@ -317,11 +317,18 @@ class DGDMModel(nn.Module):
                 self._validate_forward_inputs(data, mode, return_attention, return_embeddings)
         except Exception as e:
             raise ModelInferenceError(f"Input validation failed: {e}")
-        if (self.training or torch.is_grad_enabled()) and mode in ("pretrain", "finetune") and not DGDMModel._warned_no_grad:
-            # the backward kernels are SURVEY §8(f) rank 1: say so instead of silently returning graph-less losses
-            DGDMModel._warned_no_grad = True
-            warnings.warn("dgdm_histopath_lab_b200 computes the forward only: outputs carry no autograd graph and dropout is "
-                          "the identity (eval semantics) even in train() mode; loss.backward() will not reach the parameters")
+        if torch.is_grad_enabled() and mode in ("pretrain", "finetune") and any(p.requires_grad for p in self.parameters()):
+            # training entry points (models/dgdm_model.py:405-506 under autograd): the differentiable path of train.py — hand-written
+            # forward AND backward kernels for the GEMMs, the message passing and the spatial attention
+            if self._comm is None and (getattr(data, "batch", None) is None or get_context(data, self._num_nodes(data)).sorted):
+                from .train import train_forward
+                try:
+                    return train_forward(self, data, mode, return_embeddings, rng)
+                except Exception as e:
+                    raise ModelInferenceError(f"Forward pass failed: {e}") from e
+            if not DGDMModel._warned_no_grad:
+                DGDMModel._warned_no_grad = True
+                warnings.warn("node-partitioned / unsorted-batch forwards run the inference kernels only: outputs carry no autograd graph")
         try:
             with torch.no_grad():
                 return self._forward_impl(data, mode, return_attention, return_embeddings, rng)

@@ -179,6 +179,16 @@ int dgdm_mha_dense(const float* q, int ldq, const float* k, int ldk, const float
                    const float* pos_k, int pos_by_head, float temperature, float* out, int ldo, float* weights,
                    int per_head, void* stream);
 
+/* Backward of dgdm_spatial_attention for the training step (models/dgdm_model.py:447-480 runs this layer under
+ * autograd): given qkv [N,3D], positions, the forward output O and its gradient dO, returns dqkv [N,3D] (dq | dk | dv).
+ * Self-attention inside each graph segment (seg_of[i] = segment of row i, seg_ptr = segment bounds). lse / delta: [N, heads] scratch
+ * (log-sum-exp of the scores and O.dO per row and head, recomputed here — the forward keeps no softmax statistics).
+ * head_dim 16 only (DGDM-Base). Exact fp32, deterministic (no atomics). */
+int dgdm_spatial_attention_backward(const float* qkv, int ld, const float* pos, const int* seg_of, const int* seg_ptr,
+                                    int N, int D, int heads, float temperature, const float* O, int ldo,
+                                    const float* dO, int lddo, float* lse, float* delta, float* dqkv, int ldd,
+                                    void* stream);
+
 /* GlobalAttentionPool (models/dgdm_model.py:588-615): one query (q_tok = q_proj(global_token), [D]) per graph
  * over that graph's keys/values kv [N, 2*D] (k|v). out [num_seg, D] before out_proj.
  * work: dgdm_attention_pool_work_floats(N,D,heads,num_seg) floats. Empty segments give zeros. */

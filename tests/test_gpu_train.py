@@ -1,0 +1,130 @@
+"""Training path: backward kernels and the pretrain step under autograd, against torch autograd of dense /
+oracle restatements on identical inputs. Tolerances: gradients rel 2e-4 of the tensor's max |grad| (fp32 summation order)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from dgdm_histopath_lab_b200 import ops, synth
+from dgdm_histopath_lab_b200 import train as T
+from oracle import dgdm_oracle as O
+from util import SMALL_CFG, golden, make_model, oracle_cfg, rel_err, sd_cpu
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_attention_backward_vs_dense_autograd():
+    g = torch.Generator().manual_seed(0)
+    segs = [0, 150, 150 + 77, 150 + 77 + 201]
+    n, H, hd = segs[-1], 8, 16
+    D = H * hd
+    qkv = torch.randn(n, 3 * D, generator=g)
+    pos = torch.rand(n, 2, generator=g) * 2
+    go = torch.randn(n, D, generator=g)
+    ref_q = qkv.clone().double().requires_grad_(True)
+    outs = []
+    for a, b in zip(segs[:-1], segs[1:]):
+        q = ref_q[a:b, :D].view(-1, H, hd); k = ref_q[a:b, D:2 * D].view(-1, H, hd); v = ref_q[a:b, 2 * D:].view(-1, H, hd)
+        s = torch.einsum("qhd,khd->hqk", q, k) / math.sqrt(hd) - torch.cdist(pos[a:b].double(), pos[a:b].double()).unsqueeze(0) / 0.7
+        outs.append(torch.einsum("hqk,khd->qhd", torch.softmax(s, -1), v).reshape(-1, D))
+    ref_o = torch.cat(outs)
+    ref_o.backward(go.double())
+    seg_ptr = torch.tensor(segs, dtype=torch.int32, device=DEV)
+    seg_of = torch.repeat_interleave(torch.arange(3, dtype=torch.int32), torch.tensor([150, 77, 201])).to(DEV)
+    x = qkv.to(DEV).requires_grad_(True)
+    o = T._SpatialAttnFn.apply(x, pos.to(DEV), seg_ptr, seg_of, 3, H, 0.7, 201)
+    assert rel_err(o, ref_o)[0] < 2e-5
+    o.backward(go.to(DEV))
+    assert rel_err(x.grad, ref_q.grad)[0] < 2e-5
+
+
+def test_spmm_backward_is_transposed_spmm():
+    d = synth.tile_graph(700, 8, seed=2).to(DEV)
+    csr = ops.csr_build(d.edge_index, 700)
+    csr_t = T.transpose_csr(csr)
+    g = torch.Generator().manual_seed(1)
+    h = torch.randn(700, 64, generator=g).to(DEV).requires_grad_(True)
+    add = torch.randn(700, 64, generator=g).to(DEV).requires_grad_(True)
+    bias = torch.randn(64, generator=g).to(DEV).requires_grad_(True)
+    go = torch.randn(700, 64, generator=g).to(DEV)
+    out = T._SpmmFn.apply(h, add, bias, csr, csr_t, 700)
+    out.backward(go)
+    # dense restatement: A_hat = D^-1/2 (A + I) D^-1/2 with multi-edges counted (core/graph_layers.py:76-84)
+    ei = d.edge_index.cpu()
+    A = torch.zeros(700, 700, dtype=torch.float64)
+    A.index_put_((ei[1], ei[0]), torch.ones(ei.size(1), dtype=torch.float64), accumulate=True)
+    A += torch.eye(700, dtype=torch.float64)
+    dinv = A.sum(1).pow(-0.5)
+    A = dinv[:, None] * A * dinv[None, :]
+    assert rel_err(out, A @ h.detach().cpu().double() + add.detach().cpu().double() + bias.detach().cpu().double())[0] < 2e-5
+    assert rel_err(h.grad, A.t() @ go.cpu().double())[0] < 2e-5
+    assert torch.equal(add.grad, go) and rel_err(bias.grad, go.sum(0))[0] < 1e-5
+
+
+def test_linear_backward():
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(333, 96, generator=g).to(DEV).requires_grad_(True)
+    w = torch.randn(48, 96, generator=g).to(DEV).requires_grad_(True)
+    b = torch.randn(48, generator=g).to(DEV).requires_grad_(True)
+    go = torch.randn(333, 48, generator=g).to(DEV)
+    T.linear(x, w, b).backward(go)
+    xd, wd, god = x.detach().double(), w.detach().double(), go.double()
+    assert rel_err(x.grad, god @ wd)[0] < 2e-5 and rel_err(w.grad, god.t() @ xd)[0] < 2e-5 and rel_err(b.grad, god.sum(0))[0] < 2e-5
+
+
+def test_pretrain_step_loss_and_gradients_vs_oracle_autograd():
+    """config 5 parity case: entity masking + forward(mode='pretrain') + backward with the reference's RNG draws injected; loss,
+    global gradient norm and every parameter gradient against torch autograd through the CPU oracle."""
+    gd = golden("pretrain_step.npz")
+    m = make_model(SMALL_CFG).eval()                       # eval(): dropout off, BatchNorm statistics frozen — grad still flows
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in m.state_dict().items()}
+    b = synth.tile_batch(2, 150, 48, seed=11)
+    rng = dict(mask_indices=torch.tensor(gd["mask_indices"]), mask_token=torch.tensor(gd["mask_token"]),
+               timesteps=torch.tensor(gd["timesteps"]), noise=list(torch.tensor(gd["noise"]).split(150)),
+               target=list(torch.tensor(gd["target"]).split(150)))
+    ref = O.pretrain_step(sd, oracle_cfg(SMALL_CFG), b.x, b.edge_index, None, b.batch, b.pos, rng=rng)
+    ref["total_pretrain_loss"].backward()
+    mg = m.to(DEV)
+    rng_g = dict(rng, noise=torch.tensor(gd["noise"]), target=torch.tensor(gd["target"]))
+    out = mg.pretrain_step(b.to(DEV), mask_ratio=0.15, rng=rng_g)
+    loss = out["total_pretrain_loss"]
+    assert loss.requires_grad
+    assert abs(float(loss) - float(gd["total_pretrain_loss"])) < 1e-4 * abs(float(gd["total_pretrain_loss"]))
+    loss.backward()
+    worst, n_cmp, sq_ref, sq_our = 0.0, 0, 0.0, 0.0
+    for name, p in mg.named_parameters():
+        gr = sd[name].grad
+        if gr is None or float(gr.abs().max()) == 0.0:
+            assert p.grad is None or float(p.grad.abs().max()) < 1e-7, f"{name}: gradient where the reference has none"
+            continue
+        assert p.grad is not None, f"{name}: missing gradient"
+        e = rel_err(p.grad, gr)[0]
+        worst = max(worst, e)
+        n_cmp += 1
+        sq_ref += float(gr.double().pow(2).sum()); sq_our += float(p.grad.double().pow(2).sum())
+        assert e < 5e-4, f"{name}: gradient rel err {e}"
+    print(f"{n_cmp} parameter gradients compared, worst rel err {worst:.2e}, grad norm ours {math.sqrt(sq_our):.6f} ref {math.sqrt(sq_ref):.6f}")
+    assert n_cmp > 100 and abs(math.sqrt(sq_our) - math.sqrt(sq_ref)) < 1e-4 * math.sqrt(sq_ref)
+
+
+def test_training_loop_reduces_the_loss():
+    torch.manual_seed(0)
+    m = make_model(SMALL_CFG).to(DEV).train()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    b = synth.tile_batch(2, 150, 48, seed=11).to(DEV)
+    g = torch.Generator().manual_seed(5)
+    rng = dict(timesteps=torch.tensor([3, 7]), noise=torch.randn(300, 32, generator=g), target=torch.randn(300, 32, generator=g))
+    opt = torch.optim.Adam(m.parameters(), lr=2e-3)
+    losses = []
+    for _ in range(12):
+        opt.zero_grad()
+        loss = m(b, mode="pretrain", rng=rng)["diffusion_loss"]
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    print("losses", [round(v, 4) for v in losses])
+    assert losses[-1] < 0.9 * losses[0]

@@ -43,7 +43,10 @@ class _LinearFn(torch.autograd.Function):
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             if _gemm_ok(w.size(1), w.size(0)):
-                gx = ops.linear(gy, ops.SplitWeight(w.detach().t().contiguous()))          # dX = dY W on the tcgen05 kernel
+                # dX = dY W on the tcgen05 kernel. The split-fp16 operands need A in the NORMAL fp16 range (activations are O(1),
+                # gradients are ~1e-6 and would lose their lo plane): scale by an exact power of two on the device, undo afterwards
+                sc = torch.exp2(torch.round(torch.log2(8.0 / gy.abs().amax().clamp_min(1e-30))))
+                gx = ops.linear(gy * sc, ops.SplitWeight(w.detach().t().contiguous())) / sc
             else:
                 gx = gy @ w
         if ctx.needs_input_grad[1]:

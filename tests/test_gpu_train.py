@@ -63,12 +63,14 @@ def test_spmm_backward_is_transposed_spmm():
     assert torch.equal(add.grad, go) and rel_err(bias.grad, go.sum(0))[0] < 1e-5
 
 
-def test_linear_backward():
+@pytest.mark.parametrize("gscale", [1.0, 1e-7])
+def test_linear_backward(gscale):
+    """gscale 1e-7: gradients far below the fp16 normal range must keep fp32-class accuracy (power-of-two prescale of dY)"""
     g = torch.Generator().manual_seed(2)
     x = torch.randn(333, 96, generator=g).to(DEV).requires_grad_(True)
     w = torch.randn(48, 96, generator=g).to(DEV).requires_grad_(True)
     b = torch.randn(48, generator=g).to(DEV).requires_grad_(True)
-    go = torch.randn(333, 48, generator=g).to(DEV)
+    go = (torch.randn(333, 48, generator=g) * gscale).to(DEV)
     T.linear(x, w, b).backward(go)
     xd, wd, god = x.detach().double(), w.detach().double(), go.double()
     assert rel_err(x.grad, god @ wd)[0] < 2e-5 and rel_err(w.grad, god.t() @ xd)[0] < 2e-5 and rel_err(b.grad, god.sum(0))[0] < 2e-5
@@ -93,10 +95,10 @@ def test_pretrain_step_loss_and_gradients_vs_oracle_autograd():
     assert loss.requires_grad
     assert abs(float(loss) - float(gd["total_pretrain_loss"])) < 1e-4 * abs(float(gd["total_pretrain_loss"]))
     loss.backward()
-    worst, n_cmp, sq_ref, sq_our = 0.0, 0, 0.0, 0.0
+    worst, n_cmp, sq_ref, sq_our, bad = 0.0, 0, 0.0, 0.0, []
     for name, p in mg.named_parameters():
         gr = sd[name].grad
-        if gr is None or float(gr.abs().max()) == 0.0:
+        if gr is None or float(gr.abs().max()) < 1e-9:        # unused parameters, and k_proj.bias (softmax is invariant to a key bias)
             assert p.grad is None or float(p.grad.abs().max()) < 1e-7, f"{name}: gradient where the reference has none"
             continue
         assert p.grad is not None, f"{name}: missing gradient"
@@ -104,7 +106,10 @@ def test_pretrain_step_loss_and_gradients_vs_oracle_autograd():
         worst = max(worst, e)
         n_cmp += 1
         sq_ref += float(gr.double().pow(2).sum()); sq_our += float(p.grad.double().pow(2).sum())
-        assert e < 5e-4, f"{name}: gradient rel err {e}"
+        if e >= 5e-4:
+            bad.append((name, round(e, 5)))
+    print("parameters with gradient error >= 5e-4:", bad[:12])
+    assert not bad, bad[:10]
     print(f"{n_cmp} parameter gradients compared, worst rel err {worst:.2e}, grad norm ours {math.sqrt(sq_our):.6f} ref {math.sqrt(sq_ref):.6f}")
     assert n_cmp > 100 and abs(math.sqrt(sq_our) - math.sqrt(sq_ref)) < 1e-4 * math.sqrt(sq_ref)
 

@@ -387,6 +387,8 @@ def main():
                          "large = configs[3]: DGDM-Large (configs/dgdm_large.yaml) on one --nodes graph (500000 in BASELINE.json), meant for torchrun; "
                          "pretrain = configs[4]: entity-masking pretrain step (fwd + bwd + grad all-reduce + AdamW) of DGDM-Base, one --nodes graph "
                          "(50000 in BASELINE.json) per rank; builder1m = configs[2]: TissueGraphBuilder edge construction over --rows 768-d embeddings, query rows sharded over the ranks")
+    ap.add_argument("--cuda-graph", type=int, default=1, help="1: `value` replays the CUDA graph of the whole forward (CSR build included) captured by "
+                                                              "DGDMModel.graphed(); 0: eager launches")
     ap.add_argument("--no-fused-halo", action="store_true", help="multi-GPU: NCCL all-gather per propagate instead of the GEMM-epilogue P2P/multicast stores")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -466,6 +468,17 @@ def main():
     for _ in range(args.warmup):
         out = step_resident()
     barrier()
+    graphed = None
+    if args.cuda_graph and args.workload != "large":
+        try:
+            graphed = model.graphed(data, return_embeddings=True, warmup=1, rebuild_structure=True)
+            eager_step, step_resident = step_resident, graphed
+            for _ in range(2):
+                out = step_resident()
+            barrier()
+        except Exception as e:                       # capture unsupported in this configuration: keep the eager loop and say so
+            print(f"[bench] CUDA-graph capture failed, timing eager launches: {e}", file=sys.stderr)
+            graphed = None
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -517,8 +530,11 @@ def main():
         e2e = {"value": N * args.steps / dt, "unit": "nodes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": g.numel() * 4,
                "ms_per_step": 1e3 * dt / args.steps, "staging": "pinned host -> device on a side stream, one step ahead"}
 
-    # ---- per-kernel-class timing pass (CUDA events after every C-ABI call on the launching stream)
+    # ---- per-kernel-class timing pass (CUDA events after every C-ABI call on the launching stream; eager launches)
     pk = peaks()
+    if graphed is not None:
+        step_resident = eager_step
+        launches = args.steps * graphed.launches
     ops.profile_begin()
     step_resident()
     prof = ops.profile_end()
@@ -620,6 +636,7 @@ def main():
                                           f"of projected rows per propagate (halo), context-parallel attention, replicated graph structure",
                            "edge_cut_fraction": edge_cut, "halo_bytes_received_per_rank_per_forward": halo_bytes,
                            "value_includes": "whole forward incl. CSR build (structure cache dropped every step)",
+                           "cuda_graph": graphed is not None,
                            "attention_precise": ops.attention_precise_default(), "gemm": ops.gemm_mode(),
                            "halo": None if world == 1 else type(model._comm).__name__ + ("/multicast" if getattr(model._comm, "multicast", False) else "")},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "roofline_hbm": roof_hbm, "roofline_gemm": roof_gemm,

@@ -78,6 +78,26 @@ __device__ __forceinline__ void tile_range(const AttnBwdArgs& a, int row0, int& 
   hi = a.seg_ptr[s1 + 1];
 }
 
+// dP[r][c] = dO_r . v_c for this thread's 4 x 4 pairs (d outermost: 8 shared-memory reads per 16 FMAs)
+__device__ __forceinline__ void dp_tile(const float* dOs, const float* Vs, int tq, int tk, float dp[4][4]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dp[r][c] = 0.f;
+#pragma unroll
+  for (int d = 0; d < BHD; ++d) {
+    float g[4], v[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) g[r] = dOs[(tq * 4 + r) * BLD + d];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] = Vs[(tk + 16 * c) * BLD + d];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) dp[r][c] = fmaf(g[r], v[c], dp[r][c]);
+  }
+}
+
 struct BwdSmem {
   float A[BT * BLD], B[BT * BLD], C[BT * BLD], Dd[BT * BLD];
   float ax[BT], ay[BT], bx[BT], by[BT], v0[BT], v1[BT];
@@ -161,22 +181,24 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_kernel(const AttnBwdArgs a) {
     load_tile(sm.Dd, a.qkv, a.ld, k0, a.N, 2 * a.D + h * BHD, t);    // V
     load_meta(sm.bx, sm.by, sm.bs, a.pos, a.seg_of, k0, a.N, t);
     __syncthreads();
-    float s[4][4];
+    float s[4][4], dp[4][4];
     score_tile(sm.A, sm.B, sm.ax, sm.ay, sm.as, sm.bx, sm.by, sm.bs, tq, tk, a.scale, a.inv_temp, a.pos != nullptr, s);
+    dp_tile(sm.C, sm.Dd, tq, tk, dp);
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int qi = tq * 4 + r;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int ki = tk + 16 * c;
-        const float p = expf(s[r][c] - sm.v0[qi]);                   // exp(-inf) = 0 for masked pairs
-        float dp = 0.f;
+      for (int c = 0; c < 4; ++c) s[r][c] = expf(s[r][c] - sm.v0[qi]) * (dp[r][c] - sm.v1[qi]);     // dS; exp(-inf) = 0 for masked pairs
+    }
 #pragma unroll
-        for (int d = 0; d < BHD; ++d) dp = fmaf(sm.C[qi * BLD + d], sm.Dd[ki * BLD + d], dp);
-        const float ds = p * (dp - sm.v1[qi]);
+    for (int d = 0; d < BHD; ++d) {
+      float k[4];
 #pragma unroll
-        for (int d = 0; d < BHD; ++d) acc[r][d] = fmaf(ds, sm.B[ki * BLD + d], acc[r][d]);
-      }
+      for (int c = 0; c < 4; ++c) k[c] = sm.B[(tk + 16 * c) * BLD + d];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][d] = fmaf(s[r][c], k[c], acc[r][d]);
     }
   }
 #pragma unroll
@@ -219,25 +241,30 @@ __global__ void __launch_bounds__(256) attn_bwd_dkdv_kernel(const AttnBwdArgs a)
       sm.v1[t] = row < a.N ? a.delta[(size_t)row * heads + h] : 0.f;
     }
     __syncthreads();
-    float s[4][4];
+    float s[4][4], dp[4][4];
     score_tile(sm.A, sm.B, sm.ax, sm.ay, sm.as, sm.bx, sm.by, sm.bs, tq, tk, a.scale, a.inv_temp, a.pos != nullptr, s);
+    dp_tile(sm.C, sm.Dd, tq, tk, dp);
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int qi = tq * 4 + r;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const int ki = tk + 16 * c;
-        const float p = expf(s[r][c] - sm.v0[qi]);
-        float dp = 0.f;
-#pragma unroll
-        for (int d = 0; d < BHD; ++d) dp = fmaf(sm.C[qi * BLD + d], sm.Dd[ki * BLD + d], dp);
-        const float ds = p * (dp - sm.v1[qi]);
-#pragma unroll
-        for (int d = 0; d < BHD; ++d) {
-          dv[c][d] = fmaf(p, sm.C[qi * BLD + d], dv[c][d]);
-          dk[c][d] = fmaf(ds, sm.A[qi * BLD + d], dk[c][d]);
-        }
+        s[r][c] = expf(s[r][c] - sm.v0[qi]);                         // P
+        dp[r][c] = s[r][c] * (dp[r][c] - sm.v1[qi]);                 // dS
       }
+    }
+#pragma unroll
+    for (int d = 0; d < BHD; ++d) {
+      float g[4], q[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { g[r] = sm.C[(tq * 4 + r) * BLD + d]; q[r] = sm.A[(tq * 4 + r) * BLD + d]; }
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          dv[c][d] = fmaf(s[r][c], g[r], dv[c][d]);
+          dk[c][d] = fmaf(dp[r][c], q[r], dk[c][d]);
+        }
     }
   }
   // reduce over the 16 query-lanes that share this thread's keys: lane pair (xor 16) in registers, the 8 warps through smem

@@ -337,21 +337,28 @@ class DGDMModel(nn.Module):
         except Exception as e:
             raise ModelInferenceError(f"Forward pass failed: {e}") from e
 
-    def graphed(self, data, mode="inference", return_embeddings=False, warmup=2):
+    def graphed(self, data, mode="inference", return_embeddings=False, warmup=2, rebuild_structure=False):
         """CUDA-graph replay of `forward(data, mode, return_embeddings=...)` for small graphs, where the ~150 kernel launches and
         ~100 ctypes calls of a forward cost more than the kernels (host-bound below ~10k nodes). The forward is validated and
         warmed up eagerly (weight images, CSR, kernel attributes), captured once, and the returned callable replays it:
         `run = model.graphed(d); out = run()` — `out` tensors are static buffers overwritten by the next replay; the graph reads
         `data.x` / `data.pos` / `data.edge_attr` in place, so new features may be copied into those tensors between replays
-        (same graph structure). Single-GPU inference / finetune only."""
-        if self._comm is not None or mode == "pretrain":
-            raise ModelInferenceError("graphed() supports single-GPU inference / finetune forwards")
+        (same graph structure). Inference / finetune forwards; node-partitioned execution is captured too (every shape is static: the
+        pooled U-Net levels are replicated), with the NCCL all-gathers and the symmetric-memory barriers inside the graph — all ranks
+        must capture and replay in lock-step. rebuild_structure=True keeps the CSR build inside the captured forward."""
+        if mode == "pretrain":
+            raise ModelInferenceError("graphed() supports inference / finetune forwards")
         for _ in range(max(1, warmup)):
             self.forward(data, mode, False, return_embeddings)
         versions = self._weights_version()
         torch.cuda.synchronize()
+        if self._comm is not None:
+            self._comm.barrier()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        l0 = ops.LAUNCHES["kernels"]
+        with torch.no_grad(), torch.cuda.graph(graph, capture_error_mode="thread_local"):
+            if rebuild_structure and hasattr(data, "__dict__"):
+                data.__dict__.pop("_dgdm_ctx", None)
             static_out = self.forward(data, mode, False, return_embeddings, validate=False)
         model = self
 
@@ -360,7 +367,7 @@ class DGDMModel(nn.Module):
                 raise ModelInferenceError("parameters changed since graphed() captured the forward: capture again")
             graph.replay()
             return static_out
-        run.graph, run.outputs = graph, static_out
+        run.graph, run.outputs, run.launches = graph, static_out, ops.LAUNCHES["kernels"] - l0
         return run
 
     def _weights_version(self):

@@ -103,12 +103,13 @@ class GraphContext:
             self.num_graphs = 1
             self.seg_host = [0, self.N]
             self.sorted = True
+            self.seg_ptr = torch.arange(2, dtype=torch.int32, device=dev) * self.N      # device-side: capturable into a CUDA graph
         else:
             counts = torch.bincount(batch).cpu()          # one host sync per graph object (the reference does .item() per call)
             self.num_graphs = int(counts.numel())
             self.seg_host = [0] + torch.cumsum(counts, 0).tolist()
             self.sorted = bool((batch[1:] >= batch[:-1]).all().item()) if batch.numel() > 1 else True
-        self.seg_ptr = torch.tensor(self.seg_host, dtype=torch.int32, device=dev)
+            self.seg_ptr = torch.tensor(self.seg_host, dtype=torch.int32, device=dev)
         self.agg_attr = None
         self._key = None
 

@@ -357,8 +357,8 @@ class DGDMModel(nn.Module):
         graph = torch.cuda.CUDAGraph()
         l0 = ops.LAUNCHES["kernels"]
         with torch.no_grad(), torch.cuda.graph(graph, capture_error_mode="thread_local"):
-            if rebuild_structure and hasattr(data, "__dict__"):
-                data.__dict__.pop("_dgdm_ctx", None)
+            if rebuild_structure and hasattr(data, "__dict__") and getattr(data, "batch", None) is None:
+                data.__dict__.pop("_dgdm_ctx", None)          # (a batch vector needs a host read for the segment sizes: kept cached)
             static_out = self.forward(data, mode, False, return_embeddings, validate=False)
         model = self
 

@@ -469,7 +469,7 @@ def main():
         out = step_resident()
     barrier()
     graphed = None
-    if args.cuda_graph and args.workload != "large":
+    if args.cuda_graph and world == 1:
         try:
             graphed = model.graphed(data, return_embeddings=True, warmup=1, rebuild_structure=True)
             eager_step, step_resident = step_resident, graphed

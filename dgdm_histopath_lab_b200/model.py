@@ -343,17 +343,15 @@ class DGDMModel(nn.Module):
         warmed up eagerly (weight images, CSR, kernel attributes), captured once, and the returned callable replays it:
         `run = model.graphed(d); out = run()` — `out` tensors are static buffers overwritten by the next replay; the graph reads
         `data.x` / `data.pos` / `data.edge_attr` in place, so new features may be copied into those tensors between replays
-        (same graph structure). Inference / finetune forwards; node-partitioned execution is captured too (every shape is static: the
-        pooled U-Net levels are replicated), with the NCCL all-gathers and the symmetric-memory barriers inside the graph — all ranks
-        must capture and replay in lock-step. rebuild_structure=True keeps the CSR build inside the captured forward."""
-        if mode == "pretrain":
-            raise ModelInferenceError("graphed() supports inference / finetune forwards")
+        (same graph structure). Single-GPU inference / finetune forwards (capturing the node-partitioned forward — NCCL all-gathers and
+        symmetric-memory barriers inside the graph — was tried and dead-locked on a 2-GPU box: not supported).
+        rebuild_structure=True keeps the CSR build inside the captured forward."""
+        if self._comm is not None or mode == "pretrain":
+            raise ModelInferenceError("graphed() supports single-GPU inference / finetune forwards")
         for _ in range(max(1, warmup)):
             self.forward(data, mode, False, return_embeddings)
         versions = self._weights_version()
         torch.cuda.synchronize()
-        if self._comm is not None:
-            self._comm.barrier()
         graph = torch.cuda.CUDAGraph()
         l0 = ops.LAUNCHES["kernels"]
         with torch.no_grad(), torch.cuda.graph(graph, capture_error_mode="thread_local"):

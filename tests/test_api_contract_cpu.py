@@ -15,7 +15,6 @@ from util import SMALL_CFG, make_model
     dict(node_features=0), dict(node_features=20000), dict(hidden_dims=[]), dict(hidden_dims=[64, -1]), dict(attention_heads=0),
     dict(attention_heads=33), dict(hidden_dims=[64, 30], attention_heads=4), dict(dropout=0.95), dict(graph_layers=0), dict(graph_layers=21),
     dict(activation="nope"), dict(pooling="nope"), dict(diffusion_schedule="nope"), dict(normalization="nope"), dict(num_classes=1),
-    dict(normalization="batch"),            # accepted by the reference's validator, not implemented here: must be a configuration error
 ])
 def test_constructor_rejects_invalid_configuration(bad):
     cfg = dict(node_features=48, hidden_dims=[64, 32, 32], attention_heads=2, num_classes=3)
@@ -82,3 +81,12 @@ def test_diffusion_schedule_tables_match_closed_forms():
     assert torch.allclose(lin.betas, torch.linspace(0.1, 0.5, 5))
     with pytest.raises(ValueError):
         DiffusionScheduler(5, schedule="nope")
+
+
+@pytest.mark.parametrize("norm,cls", [("batch", torch.nn.BatchNorm1d), ("instance", torch.nn.InstanceNorm1d), ("graph", torch.nn.Identity)])
+def test_non_default_normalizations_construct_like_the_reference(norm, cls):
+    """models/encoders.py:93-102, 217-226: batch / instance build the torch layers, any other accepted name ("graph") is Identity"""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = DGDMModel(node_features=48, hidden_dims=[64, 32, 32], attention_heads=2, num_classes=3, normalization=norm)
+    assert isinstance(m.feature_encoder.encoder[1], cls) and isinstance(m.graph_encoder.norm_layers[0], cls)

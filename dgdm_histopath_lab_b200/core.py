@@ -85,15 +85,12 @@ def _ln(m):
     if isinstance(m, nn.LayerNorm):
         return (m.weight.detach(), m.bias.detach())
     if isinstance(m, nn.InstanceNorm1d):
-        dev = _INSTANCE_DEV[0]
+        dev = torch.device("cuda", torch.cuda.current_device())      # the module has no parameters to take the device from
         key = (m.num_features, dev)
         if key not in _UNIT_LN:
             _UNIT_LN[key] = (torch.ones(m.num_features, device=dev), torch.zeros(m.num_features, device=dev))
         return _UNIT_LN[key]
     return None
-
-
-_INSTANCE_DEV = [None]
 
 
 def _norm_act_torch(h, norm, act_name, training):
@@ -880,7 +877,6 @@ class FeatureEncoder(nn.Module):
         if self.use_residual:
             res = x if self.residual_proj is None else ops.linear(x, split_weight(self.residual_proj.weight), self.residual_proj.bias.detach())
         h = x
-        _INSTANCE_DEV[0] = x.device
         for i in range(self.num_layers):
             lin, norm = self.encoder[4 * i], self.encoder[4 * i + 1]
             last = i == self.num_layers - 1
@@ -928,7 +924,6 @@ class GraphEncoder(nn.Module):
             if part is not None:
                 agg = part.local(agg)
         h, outs = x, []
-        _INSTANCE_DEV[0] = x.device
         for i, layer in enumerate(self.graph_layers):
             norm = self.norm_layers[i]
             if isinstance(norm, nn.BatchNorm1d):

@@ -127,7 +127,8 @@ def attach_csr(data, rowptr, col, eid):
 
 def load_graph(path, device=None, pin=False):
     """data/dataset.py:190-200 `_load_graph`: .pt (torch.load), .pkl (pickle), .h5 (h5py: node_features, edge_index, edge_attr,
-    node_pos, labels — :203-240), plus .dgdm."""
+    node_pos, labels — :203-240), plus .dgdm. Like the reference, .pt / .pkl files are UNPICKLED (arbitrary code execution):
+    load them from trusted sources only; .dgdm and .h5 are plain arrays."""
     path = str(path)
     ext = os.path.splitext(path)[1]
     if ext == ".dgdm":

@@ -241,9 +241,9 @@ def _diffusion_loss(model, h, ctx, rng):
     te = linear(F.silu(linear(emb, te0.weight, te0.bias)), te2.weight, te2.bias)           # [B, hidden]
     d0, g1, d4, g5, d8 = (dl.denoise_net[i] for i in (0, 1, 4, 5, 8))
     hh = linear(torch.cat([xn, torch.repeat_interleave(te, sizes, dim=0)], dim=-1), d0.weight, d0.bias)
-    hh = F.dropout(F.silu(F.group_norm(hh, g1.num_groups, g1.weight, g1.bias, g1.eps)), 0.1, model.training)
+    hh = F.dropout(F.silu(F.group_norm(hh, g1.num_groups, g1.weight, g1.bias, g1.eps)), dl.denoise_net[3].p, model.training)
     hh = linear(hh, d4.weight, d4.bias)
-    hh = F.dropout(F.silu(F.group_norm(hh, g5.num_groups, g5.weight, g5.bias, g5.eps)), 0.1, model.training)
+    hh = F.dropout(F.silu(F.group_norm(hh, g5.num_groups, g5.weight, g5.bias, g5.eps)), dl.denoise_net[7].p, model.training)
     eps = linear(hh, d8.weight, d8.bias)
     losses = [F.mse_loss(eps[ctx.seg_host[i]:ctx.seg_host[i + 1]], target[ctx.seg_host[i]:ctx.seg_host[i + 1]]) for i in range(B)]
     a, b = ctx.seg_host[B - 1], ctx.seg_host[B]

@@ -315,3 +315,279 @@ extern "C" int dgdm_spatial_attention_backward(const float* qkv, int ld, const f
   DGDM_CHECK_LAUNCH();
   return DGDM_OK;
 }
+
+// =====================================================================================================================
+// Tensor-core version of the three passes (default; DGDM_ATTN_BWD=simt selects the exact fp32 kernels above).
+// Warp-level mma.sync m16n8k16 (fp16 operands, fp32 accumulate): a warp owns 16 rows of the CTA's 64-row tile and walks the
+// 64-row tiles of the other side. The score tile is produced directly in the orientation the next product needs
+// (S^T = K Q^T in the dK/dV pass, S = Q K^T in the dQ / stats passes), so the accumulator fragments of two adjacent 8-column tiles
+// ARE the A fragment of the following product (P^T dO, dS^T Q, dS K) — no shuffles, no shared-memory round trip.
+// Precision: single fp16 operand planes (q, k, v, dO, P, dS), fp32 accumulation, dO pre-scaled by a power of two (go_scale) so
+// that gradients of ~1e-6 sit in the normal fp16 range. Gradients are within ~2e-3 of the fp32 path (stated tensor-core
+// tolerance; the forward keeps its fp32-class split arithmetic because the top-k pooling downstream needs it, a gradient does not).
+namespace dgdm {
+
+constexpr int MT = 64;             // rows per CTA tile (4 warps x 16)
+constexpr int TS = 72;             // half stride of the transposed tiles (144 B: conflict-free fragment loads)
+
+__device__ __forceinline__ void mma16816(float c[4], const uint32_t a[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+struct TcSmem {
+  __half rowm[2][MT * 16];          // two row-major [64][16] tiles (B operands with k = head dim)
+  __half tr[2][16 * TS];            // two transposed [16][64(+8)] tiles (B operands with k = rows of the other side)
+  float px[MT], py[MT], v0[MT], v1[MT];
+  int sg[MT];
+};
+
+// fp32 [64 x 16] tile (rows row0.., columns col0..) -> half, row-major and/or transposed; `mul` scales the values
+__device__ __forceinline__ void tc_load(const float* src, int ld, int row0, int N, int col0, float mul, __half* rm, __half* tr, int t) {
+  for (int i = t; i < MT * 4; i += 128) {
+    const int r = i >> 2, c = (i & 3) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row0 + r < N) v = ldg4(src + (size_t)(row0 + r) * ld + col0 + c);
+    const __half h0 = __float2half_rn(v.x * mul), h1 = __float2half_rn(v.y * mul), h2 = __float2half_rn(v.z * mul), h3 = __float2half_rn(v.w * mul);
+    if (rm) { rm[r * 16 + c] = h0; rm[r * 16 + c + 1] = h1; rm[r * 16 + c + 2] = h2; rm[r * 16 + c + 3] = h3; }
+    if (tr) { tr[c * TS + r] = h0; tr[(c + 1) * TS + r] = h1; tr[(c + 2) * TS + r] = h2; tr[(c + 3) * TS + r] = h3; }
+  }
+}
+// A fragment (16 rows x 16 dims) of this warp's rows straight from global fp32
+__device__ __forceinline__ void tc_afrag(const float* src, int ld, int row0, int N, int col0, float mul, int g, int tq, uint32_t a[4]) {
+  auto ld2 = [&](int r, int c) {
+    float2 v = make_float2(0.f, 0.f);
+    if (row0 + r < N) v = *reinterpret_cast<const float2*>(src + (size_t)(row0 + r) * ld + col0 + c);
+    return pack_half2(v.x * mul, v.y * mul);
+  };
+  a[0] = ld2(g, 2 * tq); a[1] = ld2(g + 8, 2 * tq); a[2] = ld2(g, 2 * tq + 8); a[3] = ld2(g + 8, 2 * tq + 8);
+}
+
+// ---- dK / dV: CTA = (key tile, head); warp = 16 keys; loop over query tiles
+__global__ void __launch_bounds__(128) attn_bwd_dkdv_tc_kernel(const AttnBwdArgs a, const float* __restrict__ go_scale) {
+  __shared__ TcSmem sm;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31, g = lane >> 2, tq = lane & 3;
+  const int h = blockIdx.y, k0 = blockIdx.x * MT, heads = a.D / BHD;
+  const float gs = *go_scale;
+  const int kr0 = k0 + warp * 16;                                   // this warp's keys: kr0 + g, kr0 + g + 8
+  uint32_t kf[4], vf[4];
+  tc_afrag(a.qkv, a.ld, kr0, a.N, a.D + h * BHD, 1.0f, g, tq, kf);
+  tc_afrag(a.qkv, a.ld, kr0, a.N, 2 * a.D + h * BHD, 1.0f, g, tq, vf);
+  float kx[2], ky[2]; int ks[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int key = kr0 + g + 8 * r;
+    kx[r] = (a.pos && key < a.N) ? a.pos[2 * (size_t)key] : 0.f;
+    ky[r] = (a.pos && key < a.N) ? a.pos[2 * (size_t)key + 1] : 0.f;
+    ks[r] = key < a.N ? a.seg_of[key] : -1000000 - key;
+  }
+  float dv[2][4], dk[2][4];
+#pragma unroll
+  for (int n = 0; n < 2; ++n)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { dv[n][i] = 0.f; dk[n][i] = 0.f; }
+  int lo, hi;
+  tile_range(a, k0, lo, hi);
+  const bool use_pos = a.pos != nullptr;
+  for (int q0 = lo; q0 < hi; q0 += MT) {
+    __syncthreads();
+    tc_load(a.qkv, a.ld, q0, a.N, h * BHD, 1.0f, sm.rowm[0], sm.tr[0], t);          // Q, Q^T
+    tc_load(a.dO, a.lddo, q0, a.N, h * BHD, gs, sm.rowm[1], sm.tr[1], t);            // dO, dO^T (scaled)
+    if (t < MT) {
+      const int row = q0 + t;
+      sm.px[t] = (use_pos && row < a.N) ? a.pos[2 * (size_t)row] : 0.f;
+      sm.py[t] = (use_pos && row < a.N) ? a.pos[2 * (size_t)row + 1] : 0.f;
+      sm.sg[t] = row < a.N ? a.seg_of[row] : -1 - t;
+      sm.v0[t] = row < a.N ? a.lse[(size_t)row * heads + h] : 0.f;
+      sm.v1[t] = row < a.N ? a.delta[(size_t)row * heads + h] * gs : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kstep = 0; kstep < 4; ++kstep) {                         // 16 queries per step = two 8-query tiles
+      uint32_t pf[4], sf[4];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int qb = kstep * 16 + half * 8;                         // B fragment: queries qb + g, dims 2 tq (+8)
+        const uint32_t* qrow = reinterpret_cast<const uint32_t*>(sm.rowm[0] + (qb + g) * 16);
+        const uint32_t* grow = reinterpret_cast<const uint32_t*>(sm.rowm[1] + (qb + g) * 16);
+        float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+        mma16816(s, kf, qrow[tq], qrow[tq + 4]);                      // S^T[key, query]
+        mma16816(dp, vf, grow[tq], grow[tq + 4]);                     // dP^T[key, query] = v_key . dO_query
+        float p[4], ds[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                                 // i: (key g + 8 (i>>1), query qb + 2 tq + (i&1))
+          const int r = i >> 1, qi = qb + 2 * tq + (i & 1);
+          float v = s[i] * a.scale;
+          if (use_pos) { const float dx = sm.px[qi] - kx[r], dy = sm.py[qi] - ky[r]; v -= sqrtf(dx * dx + dy * dy) * a.inv_temp; }
+          p[i] = (sm.sg[qi] == ks[r]) ? __expf(v - sm.v0[qi]) : 0.f;
+          ds[i] = p[i] * (dp[i] - sm.v1[qi]);
+        }
+        pf[2 * half] = pack_half2(p[0], p[1]); pf[2 * half + 1] = pack_half2(p[2], p[3]);
+        sf[2 * half] = pack_half2(ds[0], ds[1]); sf[2 * half + 1] = pack_half2(ds[2], ds[3]);
+      }
+      // A fragment order is (row g, k lo), (row g+8, k lo), (row g, k hi), (row g+8, k hi): exactly pf / sf
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {                                   // dims n*8 + g
+        const uint32_t* gt = reinterpret_cast<const uint32_t*>(sm.tr[1] + (n * 8 + g) * TS + kstep * 16);
+        const uint32_t* qt = reinterpret_cast<const uint32_t*>(sm.tr[0] + (n * 8 + g) * TS + kstep * 16);
+        mma16816(dv[n], pf, gt[tq], gt[tq + 4]);                      // dV[key, dim] += P^T[key, q] dO[q, dim]
+        mma16816(dk[n], sf, qt[tq], qt[tq + 4]);                      // dK[key, dim] += dS^T[key, q] Q[q, dim]
+      }
+    }
+  }
+  const float inv = 1.0f / gs;
+#pragma unroll
+  for (int n = 0; n < 2; ++n)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int key = kr0 + g + 8 * r;
+      if (key < a.N) {
+        float* o = a.dqkv + (size_t)key * a.ldd + h * BHD + n * 8 + 2 * tq;
+        *reinterpret_cast<float2*>(o + 2 * a.D) = make_float2(dv[n][2 * r] * inv, dv[n][2 * r + 1] * inv);
+        *reinterpret_cast<float2*>(o + a.D) = make_float2(dk[n][2 * r] * inv * a.scale, dk[n][2 * r + 1] * inv * a.scale);
+      }
+    }
+}
+
+// ---- dQ (MODE 1) and the softmax statistics (MODE 0): CTA = (query tile, head); warp = 16 queries; loop over key tiles
+template <int MODE>
+__global__ void __launch_bounds__(128) attn_bwd_q_tc_kernel(const AttnBwdArgs a, const float* __restrict__ go_scale) {
+  __shared__ TcSmem sm;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31, g = lane >> 2, tq = lane & 3;
+  const int h = blockIdx.y, q0 = blockIdx.x * MT, heads = a.D / BHD;
+  const float gs = MODE ? *go_scale : 1.0f;
+  const int qr0 = q0 + warp * 16;
+  uint32_t qf[4], gf[4];
+  tc_afrag(a.qkv, a.ld, qr0, a.N, h * BHD, 1.0f, g, tq, qf);
+  if (MODE) tc_afrag(a.dO, a.lddo, qr0, a.N, h * BHD, gs, g, tq, gf);
+  float qx[2], qy[2], lse[2], dl[2]; int qs[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = qr0 + g + 8 * r;
+    qx[r] = (a.pos && row < a.N) ? a.pos[2 * (size_t)row] : 0.f;
+    qy[r] = (a.pos && row < a.N) ? a.pos[2 * (size_t)row + 1] : 0.f;
+    qs[r] = row < a.N ? a.seg_of[row] : -1000000 - row;
+    lse[r] = (MODE && row < a.N) ? a.lse[(size_t)row * heads + h] : 0.f;
+    dl[r] = (MODE && row < a.N) ? a.delta[(size_t)row * heads + h] * gs : 0.f;
+  }
+  float dq[2][4], m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+#pragma unroll
+  for (int n = 0; n < 2; ++n)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dq[n][i] = 0.f;
+  int lo, hi;
+  tile_range(a, q0, lo, hi);
+  const bool use_pos = a.pos != nullptr;
+  for (int k0 = lo; k0 < hi; k0 += MT) {
+    __syncthreads();
+    tc_load(a.qkv, a.ld, k0, a.N, a.D + h * BHD, 1.0f, sm.rowm[0], MODE ? sm.tr[0] : nullptr, t);       // K (, K^T)
+    if (MODE) tc_load(a.qkv, a.ld, k0, a.N, 2 * a.D + h * BHD, 1.0f, sm.rowm[1], nullptr, t);           // V
+    if (t < MT) {
+      const int row = k0 + t;
+      sm.px[t] = (use_pos && row < a.N) ? a.pos[2 * (size_t)row] : 0.f;
+      sm.py[t] = (use_pos && row < a.N) ? a.pos[2 * (size_t)row + 1] : 0.f;
+      sm.sg[t] = row < a.N ? a.seg_of[row] : -1 - t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kstep = 0; kstep < 4; ++kstep) {
+      uint32_t sf[4];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int kb = kstep * 16 + half * 8;
+        const uint32_t* krow = reinterpret_cast<const uint32_t*>(sm.rowm[0] + (kb + g) * 16);
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        mma16816(s, qf, krow[tq], krow[tq + 4]);                      // S[query, key]
+        float sv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                                 // i: (query g + 8 (i>>1), key kb + 2 tq + (i&1))
+          const int r = i >> 1, ki = kb + 2 * tq + (i & 1);
+          float v = s[i] * a.scale;
+          if (use_pos) { const float dx = qx[r] - sm.px[ki], dy = qy[r] - sm.py[ki]; v -= sqrtf(dx * dx + dy * dy) * a.inv_temp; }
+          sv[i] = (sm.sg[ki] == qs[r]) ? v : -INFINITY;
+        }
+        if (MODE == 0) {
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const float mx = fmaxf(sv[2 * r], sv[2 * r + 1]);
+            if (mx > m[r]) { l[r] *= __expf(m[r] - mx); m[r] = mx; }
+            if (m[r] > -INFINITY) l[r] += __expf(sv[2 * r] - m[r]) + __expf(sv[2 * r + 1] - m[r]);
+          }
+        } else {
+          const uint32_t* vrow = reinterpret_cast<const uint32_t*>(sm.rowm[1] + (kb + g) * 16);
+          float dp[4] = {0.f, 0.f, 0.f, 0.f};
+          mma16816(dp, gf, vrow[tq], vrow[tq + 4]);                   // dP[query, key] = dO_query . v_key
+          float ds[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { const int r = i >> 1; ds[i] = __expf(sv[i] - lse[r]) * (dp[i] - dl[r]); }
+          sf[2 * half] = pack_half2(ds[0], ds[1]); sf[2 * half + 1] = pack_half2(ds[2], ds[3]);
+        }
+      }
+      if (MODE) {
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+          const uint32_t* kt = reinterpret_cast<const uint32_t*>(sm.tr[0] + (n * 8 + g) * TS + kstep * 16);
+          mma16816(dq[n], sf, kt[tq], kt[tq + 4]);                    // dQ[query, dim] += dS[query, key] K[key, dim]
+        }
+      }
+    }
+  }
+  if (MODE == 0) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1) {                              // merge the 4 lanes of the quad (same row, different keys)
+        const float mo = __shfl_xor_sync(0xffffffffu, m[r], o), lo_ = __shfl_xor_sync(0xffffffffu, l[r], o);
+        const float mn = fmaxf(m[r], mo);
+        l[r] = (m[r] > -INFINITY ? l[r] * __expf(m[r] - mn) : 0.f) + (mo > -INFINITY ? lo_ * __expf(mo - mn) : 0.f);
+        m[r] = mn;
+      }
+      const int row = qr0 + g + 8 * r;
+      if (tq == 0 && row < a.N) a.lse[(size_t)row * heads + h] = m[r] + logf(l[r]);
+    }
+    if (t < MT && q0 + t < a.N) {
+      const float* o = a.O + (size_t)(q0 + t) * a.ldo + h * BHD;
+      const float* gg = a.dO + (size_t)(q0 + t) * a.lddo + h * BHD;
+      float d = 0.f;
+#pragma unroll
+      for (int j = 0; j < BHD; ++j) d = fmaf(o[j], gg[j], d);
+      a.delta[(size_t)(q0 + t) * heads + h] = d;
+    }
+  } else {
+    const float inv = a.scale / gs;
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int row = qr0 + g + 8 * r;
+        if (row < a.N)
+          *reinterpret_cast<float2*>(a.dqkv + (size_t)row * a.ldd + h * BHD + n * 8 + 2 * tq) = make_float2(dq[n][2 * r] * inv, dq[n][2 * r + 1] * inv);
+      }
+  }
+}
+
+}  // namespace dgdm
+
+extern "C" int dgdm_spatial_attention_backward_tc(const float* qkv, int ld, const float* pos, const int* seg_of, const int* seg_ptr,
+                                                  int N, int D, int heads, float temperature, const float* O, int ldo,
+                                                  const float* dO, int lddo, const float* go_scale, float* lse, float* delta,
+                                                  float* dqkv, int ldd, void* stream) {
+  if (!qkv || !seg_of || !seg_ptr || !O || !dO || !go_scale || !lse || !delta || !dqkv) return DGDM_ERR_INVALID;
+  if (heads <= 0 || D != heads * BHD || !(temperature > 0.f) || (ld % 4) || (ldo % 4) || (lddo % 4) || (ldd % 2)) return DGDM_ERR_INVALID;
+  if (N <= 0) return DGDM_OK;
+  AttnBwdArgs a;
+  a.qkv = qkv; a.ld = ld; a.pos = pos; a.seg_of = seg_of; a.seg_ptr = seg_ptr; a.N = N; a.D = D;
+  a.scale = 1.0f / sqrtf((float)BHD); a.inv_temp = 1.0f / temperature;
+  a.O = O; a.ldo = ldo; a.dO = dO; a.lddo = lddo; a.lse = lse; a.delta = delta; a.dqkv = dqkv; a.ldd = ldd;
+  const dim3 grid((N + MT - 1) / MT, heads);
+  cudaStream_t s = (cudaStream_t)stream;
+  attn_bwd_q_tc_kernel<0><<<grid, 128, 0, s>>>(a, go_scale);
+  attn_bwd_dkdv_tc_kernel<<<grid, 128, 0, s>>>(a, go_scale);
+  attn_bwd_q_tc_kernel<1><<<grid, 128, 0, s>>>(a, go_scale);
+  DGDM_CHECK_LAUNCH();
+  return DGDM_OK;
+}

@@ -21,7 +21,7 @@ KERNELS_PER_CALL = {
     "dgdm_spmm_gcn": 1, "dgdm_edge_attr_aggregate": 1, "dgdm_topk_select": 12, "dgdm_pool_gather": 1, "dgdm_csr_pool": 5,
     "dgdm_unpool_add_act": 1, "dgdm_segment_softmax_scores": 1, "dgdm_segment_minmax": 1, "dgdm_spatial_pe_add": 1,
     "dgdm_spatial_attention": 6, "dgdm_spatial_attention_weights": 1, "dgdm_attention_pool": 2, "dgdm_diffusion_add_noise": 1,
-    "dgdm_groupnorm_silu": 1, "dgdm_ddpm_update": 1, "dgdm_spatial_attention_backward": 3, "dgdm_mha_dense": 1,
+    "dgdm_groupnorm_silu": 1, "dgdm_ddpm_update": 1, "dgdm_spatial_attention_backward": 3, "dgdm_spatial_attention_backward_tc": 3, "dgdm_mha_dense": 1,
     "dgdm_row_normalize": 1, "dgdm_contrastive_accumulate": 1, "dgdm_validate_inputs": 1, "dgdm_knn_cosine": 4, "dgdm_knn2d": 2,
     "dgdm_row_sqnorm_f64": 1, "dgdm_knn_cosine_tc": 6,
 }
@@ -374,15 +374,28 @@ def spatial_attention_any(qkv, pos, seg_ptr, num_seg, heads, temperature=1.0, *,
     return out
 
 
-def spatial_attention_backward(qkv, pos, seg_of, seg_ptr, heads, temperature, out, grad_out):
-    """d(qkv) of the spatial self-attention core (training path). qkv [N, 3D], out / grad_out [N, D]; seg_of int32 [N]."""
+def attention_backward_mode():
+    return os.environ.get("DGDM_ATTN_BWD", "tc")
+
+
+def spatial_attention_backward(qkv, pos, seg_of, seg_ptr, heads, temperature, out, grad_out, mode=None):
+    """d(qkv) of the spatial self-attention core (training path). qkv [N, 3D], out / grad_out [N, D]; seg_of int32 [N].
+    mode "tc" (default): mma.sync tensor-core passes, fp16 operands (~2e-3); "simt": exact fp32 CUDA-core passes."""
     lib = _lib.load()
+    mode = mode or attention_backward_mode()
     N, D3 = qkv.shape
     D = D3 // 3
     dqkv = torch.empty(N, D3, dtype=torch.float32, device=qkv.device)
     lse = torch.empty(N, heads, dtype=torch.float32, device=qkv.device)
     delta = torch.empty(N, heads, dtype=torch.float32, device=qkv.device)
     go = _f32c(grad_out.contiguous())
+    if mode == "tc":
+        sc = torch.exp2(torch.round(torch.log2(8.0 / go.abs().amax().clamp_min(1e-30)))).reshape(1).contiguous()
+        _check(lib.dgdm_spatial_attention_backward_tc(_p(_f32c(qkv)), qkv.stride(0), _p(pos), _p(seg_of), _p(seg_ptr), N, D, heads,
+                                                      float(temperature), _p(_f32c(out)), out.stride(0), _p(go), go.stride(0), _p(sc),
+                                                      _p(lse), _p(delta), _p(dqkv), dqkv.stride(0), _stream()),
+               "dgdm_spatial_attention_backward_tc")
+        return dqkv
     _check(lib.dgdm_spatial_attention_backward(_p(_f32c(qkv)), qkv.stride(0), _p(pos), _p(seg_of), _p(seg_ptr), N, D, heads,
                                                float(temperature), _p(_f32c(out)), out.stride(0), _p(go), go.stride(0), _p(lse),
                                                _p(delta), _p(dqkv), dqkv.stride(0), _stream()), "dgdm_spatial_attention_backward")

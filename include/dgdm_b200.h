@@ -189,6 +189,15 @@ int dgdm_spatial_attention_backward(const float* qkv, int ld, const float* pos, 
                                     const float* dO, int lddo, float* lse, float* delta, float* dqkv, int ldd,
                                     void* stream);
 
+/* Tensor-core version of the same three passes (warp-level mma.sync m16n8k16, single fp16 operand planes, fp32 accumulation; the
+ * default of the training path). go_scale: device scalar, a power of two that brings max|dO| to ~8 (gradients of ~1e-6 would
+ * otherwise fall below the normal fp16 range); the outputs are un-scaled. Gradients agree with the fp32 path to ~2e-3 (stated
+ * tensor-core tolerance), deterministic. */
+int dgdm_spatial_attention_backward_tc(const float* qkv, int ld, const float* pos, const int* seg_of, const int* seg_ptr,
+                                       int N, int D, int heads, float temperature, const float* O, int ldo,
+                                       const float* dO, int lddo, const float* go_scale, float* lse, float* delta,
+                                       float* dqkv, int ldd, void* stream);
+
 /* GlobalAttentionPool (models/dgdm_model.py:588-615): one query (q_tok = q_proj(global_token), [D]) per graph
  * over that graph's keys/values kv [N, 2*D] (k|v). out [num_seg, D] before out_proj.
  * work: dgdm_attention_pool_work_floats(N,D,heads,num_seg) floats. Empty segments give zeros. */

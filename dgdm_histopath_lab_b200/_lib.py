@@ -62,9 +62,11 @@ SIGNATURES = {
                                C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, c_void_p, c_void_p, c_void_p, c_int, c_float,
                                c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "dgdm_spatial_attention_backward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_int,
-                                                c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+                                                c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "dgdm_spatial_attention_backward_tc": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_int,
-                                                   c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+                                                   c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "dgdm_spatial_attention_lse": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                                           c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dgdm_attention_pool_work_floats": (c_size_t, [c_int, c_int, c_int, c_int]),
     "dgdm_attention_pool": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dgdm_diffusion_add_noise": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

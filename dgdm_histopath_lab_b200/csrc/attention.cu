@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) spatial_attn_kernel(const Attn
 // merge key-split partials: out[r, c] = sum_s O_s 2^(m_s - m) / sum_s l_s 2^(m_s - m)
 __global__ void __launch_bounds__(256) attn_combine_kernel(const float* __restrict__ Opart, const float* __restrict__ Mpart,
                                                            const float* __restrict__ Lpart, int nsplit, int Nq, int D, int heads,
-                                                           float* __restrict__ out, int ldo) {
+                                                           float* __restrict__ out, int ldo, float* __restrict__ lse_out) {
   const int hd = D / heads;
   const size_t total = (size_t)Nq * (D / 4);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -319,6 +319,8 @@ __global__ void __launch_bounds__(256) attn_combine_kernel(const float* __restri
     }
     const float inv = l > 0.f ? 1.0f / l : 0.f;
     *reinterpret_cast<float4*>(out + (size_t)r * ldo + c) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    // log-sum-exp of the row's scores in natural units (m is a log2-domain reference, l the sum of 2^(s - m)): saved for the backward
+    if (lse_out != nullptr && c == h * hd) lse_out[(size_t)r * heads + h] = (m + log2f(l)) * 0.6931471805599453f;
   }
 }
 
@@ -567,8 +569,8 @@ static int choose_nsplit(int Nq, int Nkv, int num_seg) {
 }
 
 void attn_launch_combine(const float* Opart, const float* Mpart, const float* Lpart, int nsplit, int Nq, int D, int heads,
-                         float* out, int ldo, cudaStream_t s) {
-  attn_combine_kernel<<<agrid((size_t)Nq * (D / 4)), 256, 0, s>>>(Opart, Mpart, Lpart, nsplit, Nq, D, heads, out, ldo);
+                         float* out, int ldo, float* lse_out, cudaStream_t s) {
+  attn_combine_kernel<<<agrid((size_t)Nq * (D / 4)), 256, 0, s>>>(Opart, Mpart, Lpart, nsplit, Nq, D, heads, out, ldo, lse_out);
 }
 // attention_simt.cu: exact fp32 CUDA-core path for head dimensions other than 16 (DGDM-Large: 16 heads x 8)
 int attn_simt_launch(const float* q_qkv, int ld_q, const float* q_pos, const int* qseg_ptr, int Nq,
@@ -578,7 +580,8 @@ int attn_simt_launch(const float* q_qkv, int ld_q, const float* q_pos, const int
 size_t attn_tc_work_bytes(int Nq, int Nkv, int D, int heads, int num_seg, int max_seg_keys);
 int attn_tc_launch(const float* q_qkv, int ld_q, const float* q_pos, const int* qseg_ptr, int Nq,
                    const float* kv_qkv, int ld_kv, const float* kv_pos, const int* kseg_ptr, int Nkv,
-                   int num_seg, int max_seg_keys, float temperature, float* out, int ldo, void* work, size_t work_bytes, cudaStream_t s);
+                   int num_seg, int max_seg_keys, float temperature, float* out, int ldo, float* lse_out, void* work, size_t work_bytes,
+                   cudaStream_t s);
 
 }  // namespace dgdm
 using namespace dgdm;
@@ -602,11 +605,20 @@ extern "C" int dgdm_spatial_attention(const float* q_qkv, int ld_q, const float*
                                       const float* kv_qkv, int ld_kv, const float* kv_pos, const int* kseg_ptr, int Nkv,
                                       int num_seg, int max_seg_keys, int D, int heads, float temperature, int precise,
                                       float* out, int ldo, void* work, size_t work_bytes, void* stream) {
+  return dgdm_spatial_attention_lse(q_qkv, ld_q, q_pos, qseg_ptr, Nq, kv_qkv, ld_kv, kv_pos, kseg_ptr, Nkv, num_seg, max_seg_keys, D, heads,
+                                    temperature, precise, out, ldo, nullptr, work, work_bytes, stream);
+}
+
+extern "C" int dgdm_spatial_attention_lse(const float* q_qkv, int ld_q, const float* q_pos, const int* qseg_ptr, int Nq,
+                                          const float* kv_qkv, int ld_kv, const float* kv_pos, const int* kseg_ptr, int Nkv,
+                                          int num_seg, int max_seg_keys, int D, int heads, float temperature, int precise,
+                                          float* out, int ldo, float* lse_out, void* work, size_t work_bytes, void* stream) {
   if (!q_qkv || !kv_qkv || !qseg_ptr || !kseg_ptr || !out || !work) return DGDM_ERR_INVALID;
   if (heads <= 0 || D % heads != 0 || (ldo % 4) != 0) return DGDM_ERR_INVALID;
   if ((q_pos == nullptr) != (kv_pos == nullptr)) return DGDM_ERR_INVALID;
   if (Nq <= 0) return DGDM_OK;
   if (Nkv <= 0 || num_seg <= 0 || !(temperature > 0.f)) return DGDM_ERR_INVALID;
+  if ((D / heads != 16 || precise == 3) && lse_out != nullptr) return DGDM_ERR_INVALID;      // the CUDA-core path keeps no statistics
   if (D / heads != 16 || precise == 3)      // other head widths (DGDM-Large 16 x 8) / forced: exact fp32 CUDA-core kernel
     return attn_simt_launch(q_qkv, ld_q, q_pos, qseg_ptr, Nq, kv_qkv, ld_kv, kv_pos, kseg_ptr, num_seg, D, heads, temperature, out, ldo,
                             (cudaStream_t)stream);
@@ -614,7 +626,7 @@ extern "C" int dgdm_spatial_attention(const float* q_qkv, int ld_q, const float*
   cudaStream_t s = (cudaStream_t)stream;
   if (precise == 1 && D == 128 && heads == 8)       // product path for DGDM-Base: tcgen05 / TMEM kernel (attention_tc.cu)
     return attn_tc_launch(q_qkv, ld_q, q_pos, qseg_ptr, Nq, kv_qkv, ld_kv, kv_pos, kseg_ptr, Nkv, num_seg, max_seg_keys, temperature, out, ldo,
-                          work, work_bytes, s);
+                          lse_out, work, work_bytes, s);
   const int ns = choose_nsplit(Nq, Nkv, num_seg);
   uint8_t* w = (uint8_t*)(((uintptr_t)work + 255) & ~(uintptr_t)255);
   auto take = [&](size_t bytes) { uint8_t* r = w; w += align256(bytes); return r; };
@@ -654,7 +666,7 @@ extern "C" int dgdm_spatial_attention(const float* q_qkv, int ld_q, const float*
   if (precise) { if (full) ATT_LAUNCH(true, true); else ATT_LAUNCH(true, false); }
   else         { if (full) ATT_LAUNCH(false, true); else ATT_LAUNCH(false, false); }
 #undef ATT_LAUNCH
-  attn_combine_kernel<<<agrid((size_t)Nq * (D / 4)), 256, 0, s>>>(Opart, Mpart, Lpart, ns, Nq, D, heads, out, ldo);
+  attn_combine_kernel<<<agrid((size_t)Nq * (D / 4)), 256, 0, s>>>(Opart, Mpart, Lpart, ns, Nq, D, heads, out, ldo, lse_out);
   DGDM_CHECK_LAUNCH();
   return DGDM_OK;
 }

@@ -296,9 +296,26 @@ __global__ void __launch_bounds__(256) attn_bwd_dkdv_kernel(const AttnBwdArgs a)
 }  // namespace dgdm
 using namespace dgdm;
 
+// have_lse: lse already holds the forward's log-sum-exp (dgdm_spatial_attention_lse) -> the statistics pass only forms delta
+__global__ void __launch_bounds__(256) attn_bwd_delta_kernel(const float* __restrict__ O, int ldo, const float* __restrict__ dO, int lddo,
+                                                             int N, int heads, float* __restrict__ delta) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)N * heads) return;
+  const int row = (int)(i / heads), h = (int)(i - (size_t)row * heads);
+  const float* o = O + (size_t)row * ldo + h * dgdm::BHD;
+  const float* g = dO + (size_t)row * lddo + h * dgdm::BHD;
+  float d = 0.f;
+#pragma unroll
+  for (int j = 0; j < dgdm::BHD; j += 4) {
+    const float4 a = dgdm::ldg4(o + j), b = dgdm::ldg4(g + j);
+    d = fmaf(a.x, b.x, d); d = fmaf(a.y, b.y, d); d = fmaf(a.z, b.z, d); d = fmaf(a.w, b.w, d);
+  }
+  delta[i] = d;
+}
+
 extern "C" int dgdm_spatial_attention_backward(const float* qkv, int ld, const float* pos, const int* seg_of, const int* seg_ptr,
                                                int N, int D, int heads, float temperature, const float* O, int ldo,
-                                               const float* dO, int lddo, float* lse, float* delta, float* dqkv, int ldd,
+                                               const float* dO, int lddo, int have_lse, float* lse, float* delta, float* dqkv, int ldd,
                                                void* stream) {
   if (!qkv || !seg_of || !seg_ptr || !O || !dO || !lse || !delta || !dqkv) return DGDM_ERR_INVALID;
   if (heads <= 0 || D != heads * BHD || !(temperature > 0.f) || (ld % 4) || (ldo % 4) || (lddo % 4)) return DGDM_ERR_INVALID;
@@ -309,7 +326,8 @@ extern "C" int dgdm_spatial_attention_backward(const float* qkv, int ld, const f
   a.O = O; a.ldo = ldo; a.dO = dO; a.lddo = lddo; a.lse = lse; a.delta = delta; a.dqkv = dqkv; a.ldd = ldd;
   const dim3 grid((N + BT - 1) / BT, heads);
   cudaStream_t s = (cudaStream_t)stream;
-  attn_bwd_stats_kernel<<<grid, 256, 0, s>>>(a);
+  if (have_lse) attn_bwd_delta_kernel<<<(unsigned)(((size_t)N * heads + 255) / 256), 256, 0, s>>>(O, ldo, dO, lddo, N, heads, delta);
+  else attn_bwd_stats_kernel<<<grid, 256, 0, s>>>(a);
   attn_bwd_dkdv_kernel<<<grid, 256, 0, s>>>(a);
   attn_bwd_dq_kernel<<<grid, 256, 0, s>>>(a);
   DGDM_CHECK_LAUNCH();
@@ -342,9 +360,11 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
 struct TcSmem {
   __half rowm[2][MT * 16];          // two row-major [64][16] tiles (B operands with k = head dim)
   __half tr[2][16 * TS];            // two transposed [16][64(+8)] tiles (B operands with k = rows of the other side)
-  float px[MT], py[MT], v0[MT], v1[MT];
+  float4 meta[MT];                  // per row of the streamed tile: (x, y, lse in log2 units, delta) — one 128-bit load per row
   int sg[MT];
 };
+constexpr float LOG2E_F = 1.4426950408889634f;
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // fp32 [64 x 16] tile (rows row0.., columns col0..) -> half, row-major and/or transposed; `mul` scales the values
 __device__ __forceinline__ void tc_load(const float* src, int ld, int row0, int N, int col0, float mul, __half* rm, __half* tr, int t) {
@@ -393,17 +413,17 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_tc_kernel(const AttnBwdArgs
   int lo, hi;
   tile_range(a, k0, lo, hi);
   const bool use_pos = a.pos != nullptr;
+  const float sc2 = a.scale * LOG2E_F, it2 = a.inv_temp * LOG2E_F;
   for (int q0 = lo; q0 < hi; q0 += MT) {
     __syncthreads();
     tc_load(a.qkv, a.ld, q0, a.N, h * BHD, 1.0f, sm.rowm[0], sm.tr[0], t);          // Q, Q^T
     tc_load(a.dO, a.lddo, q0, a.N, h * BHD, gs, sm.rowm[1], sm.tr[1], t);            // dO, dO^T (scaled)
     if (t < MT) {
       const int row = q0 + t;
-      sm.px[t] = (use_pos && row < a.N) ? a.pos[2 * (size_t)row] : 0.f;
-      sm.py[t] = (use_pos && row < a.N) ? a.pos[2 * (size_t)row + 1] : 0.f;
-      sm.sg[t] = row < a.N ? a.seg_of[row] : -1 - t;
-      sm.v0[t] = row < a.N ? a.lse[(size_t)row * heads + h] : 0.f;
-      sm.v1[t] = row < a.N ? a.delta[(size_t)row * heads + h] * gs : 0.f;
+      const bool ok = row < a.N;
+      sm.meta[t] = make_float4((use_pos && ok) ? a.pos[2 * (size_t)row] : 0.f, (use_pos && ok) ? a.pos[2 * (size_t)row + 1] : 0.f,
+                               ok ? a.lse[(size_t)row * heads + h] * LOG2E_F : 0.f, ok ? a.delta[(size_t)row * heads + h] * gs : 0.f);
+      sm.sg[t] = ok ? a.seg_of[row] : -1 - t;
     }
     __syncthreads();
 #pragma unroll
@@ -418,13 +438,16 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_tc_kernel(const AttnBwdArgs
         mma16816(s, kf, qrow[tq], qrow[tq + 4]);                      // S^T[key, query]
         mma16816(dp, vf, grow[tq], grow[tq + 4]);                     // dP^T[key, query] = v_key . dO_query
         float p[4], ds[4];
+        const float4 m0 = sm.meta[qb + 2 * tq], m1 = sm.meta[qb + 2 * tq + 1];      // the two queries of this lane's columns
+        const int sg0 = sm.sg[qb + 2 * tq], sg1 = sm.sg[qb + 2 * tq + 1];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {                                 // i: (key g + 8 (i>>1), query qb + 2 tq + (i&1))
-          const int r = i >> 1, qi = qb + 2 * tq + (i & 1);
-          float v = s[i] * a.scale;
-          if (use_pos) { const float dx = sm.px[qi] - kx[r], dy = sm.py[qi] - ky[r]; v -= sqrtf(dx * dx + dy * dy) * a.inv_temp; }
-          p[i] = (sm.sg[qi] == ks[r]) ? __expf(v - sm.v0[qi]) : 0.f;
-          ds[i] = p[i] * (dp[i] - sm.v1[qi]);
+          const int r = i >> 1;
+          const float4 mq = (i & 1) ? m1 : m0;
+          float v = fmaf(s[i], sc2, -mq.z);                           // log2 units
+          if (use_pos) { const float dx = mq.x - kx[r], dy = mq.y - ky[r]; v = fmaf(sqrtf(fmaf(dx, dx, dy * dy)), -it2, v); }
+          p[i] = (((i & 1) ? sg1 : sg0) == ks[r]) ? ex2f(v) : 0.f;
+          ds[i] = p[i] * (dp[i] - mq.w);
         }
         pf[2 * half] = pack_half2(p[0], p[1]); pf[2 * half + 1] = pack_half2(p[2], p[3]);
         sf[2 * half] = pack_half2(ds[0], ds[1]); sf[2 * half + 1] = pack_half2(ds[2], ds[3]);
@@ -471,7 +494,7 @@ __global__ void __launch_bounds__(128) attn_bwd_q_tc_kernel(const AttnBwdArgs a,
     qx[r] = (a.pos && row < a.N) ? a.pos[2 * (size_t)row] : 0.f;
     qy[r] = (a.pos && row < a.N) ? a.pos[2 * (size_t)row + 1] : 0.f;
     qs[r] = row < a.N ? a.seg_of[row] : -1000000 - row;
-    lse[r] = (MODE && row < a.N) ? a.lse[(size_t)row * heads + h] : 0.f;
+    lse[r] = (MODE && row < a.N) ? a.lse[(size_t)row * heads + h] * LOG2E_F : 0.f;
     dl[r] = (MODE && row < a.N) ? a.delta[(size_t)row * heads + h] * gs : 0.f;
   }
   float dq[2][4], m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
@@ -482,15 +505,16 @@ __global__ void __launch_bounds__(128) attn_bwd_q_tc_kernel(const AttnBwdArgs a,
   int lo, hi;
   tile_range(a, q0, lo, hi);
   const bool use_pos = a.pos != nullptr;
+  const float sc2 = a.scale * LOG2E_F, it2 = a.inv_temp * LOG2E_F;
   for (int k0 = lo; k0 < hi; k0 += MT) {
     __syncthreads();
     tc_load(a.qkv, a.ld, k0, a.N, a.D + h * BHD, 1.0f, sm.rowm[0], MODE ? sm.tr[0] : nullptr, t);       // K (, K^T)
     if (MODE) tc_load(a.qkv, a.ld, k0, a.N, 2 * a.D + h * BHD, 1.0f, sm.rowm[1], nullptr, t);           // V
     if (t < MT) {
       const int row = k0 + t;
-      sm.px[t] = (use_pos && row < a.N) ? a.pos[2 * (size_t)row] : 0.f;
-      sm.py[t] = (use_pos && row < a.N) ? a.pos[2 * (size_t)row + 1] : 0.f;
-      sm.sg[t] = row < a.N ? a.seg_of[row] : -1 - t;
+      const bool ok = row < a.N;
+      sm.meta[t] = make_float4((use_pos && ok) ? a.pos[2 * (size_t)row] : 0.f, (use_pos && ok) ? a.pos[2 * (size_t)row + 1] : 0.f, 0.f, 0.f);
+      sm.sg[t] = ok ? a.seg_of[row] : -1 - t;
     }
     __syncthreads();
 #pragma unroll
@@ -502,20 +526,23 @@ __global__ void __launch_bounds__(128) attn_bwd_q_tc_kernel(const AttnBwdArgs a,
         const uint32_t* krow = reinterpret_cast<const uint32_t*>(sm.rowm[0] + (kb + g) * 16);
         float s[4] = {0.f, 0.f, 0.f, 0.f};
         mma16816(s, qf, krow[tq], krow[tq + 4]);                      // S[query, key]
-        float sv[4];
+        float sv[4];                                                  // scores in log2 units
+        const float4 m0 = sm.meta[kb + 2 * tq], m1 = sm.meta[kb + 2 * tq + 1];
+        const int sg0 = sm.sg[kb + 2 * tq], sg1 = sm.sg[kb + 2 * tq + 1];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {                                 // i: (query g + 8 (i>>1), key kb + 2 tq + (i&1))
-          const int r = i >> 1, ki = kb + 2 * tq + (i & 1);
-          float v = s[i] * a.scale;
-          if (use_pos) { const float dx = qx[r] - sm.px[ki], dy = qy[r] - sm.py[ki]; v -= sqrtf(dx * dx + dy * dy) * a.inv_temp; }
-          sv[i] = (sm.sg[ki] == qs[r]) ? v : -INFINITY;
+          const int r = i >> 1;
+          const float4 mk = (i & 1) ? m1 : m0;
+          float v = s[i] * sc2;
+          if (use_pos) { const float dx = qx[r] - mk.x, dy = qy[r] - mk.y; v = fmaf(sqrtf(fmaf(dx, dx, dy * dy)), -it2, v); }
+          sv[i] = (((i & 1) ? sg1 : sg0) == qs[r]) ? v : -INFINITY;
         }
         if (MODE == 0) {
 #pragma unroll
           for (int r = 0; r < 2; ++r) {
             const float mx = fmaxf(sv[2 * r], sv[2 * r + 1]);
-            if (mx > m[r]) { l[r] *= __expf(m[r] - mx); m[r] = mx; }
-            if (m[r] > -INFINITY) l[r] += __expf(sv[2 * r] - m[r]) + __expf(sv[2 * r + 1] - m[r]);
+            if (mx > m[r]) { l[r] *= ex2f(m[r] - mx); m[r] = mx; }
+            if (m[r] > -INFINITY) l[r] += ex2f(sv[2 * r] - m[r]) + ex2f(sv[2 * r + 1] - m[r]);
           }
         } else {
           const uint32_t* vrow = reinterpret_cast<const uint32_t*>(sm.rowm[1] + (kb + g) * 16);
@@ -523,7 +550,7 @@ __global__ void __launch_bounds__(128) attn_bwd_q_tc_kernel(const AttnBwdArgs a,
           mma16816(dp, gf, vrow[tq], vrow[tq + 4]);                   // dP[query, key] = dO_query . v_key
           float ds[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { const int r = i >> 1; ds[i] = __expf(sv[i] - lse[r]) * (dp[i] - dl[r]); }
+          for (int i = 0; i < 4; ++i) { const int r = i >> 1; ds[i] = ex2f(sv[i] - lse[r]) * (dp[i] - dl[r]); }
           sf[2 * half] = pack_half2(ds[0], ds[1]); sf[2 * half + 1] = pack_half2(ds[2], ds[3]);
         }
       }
@@ -543,11 +570,11 @@ __global__ void __launch_bounds__(128) attn_bwd_q_tc_kernel(const AttnBwdArgs a,
       for (int o = 1; o <= 2; o <<= 1) {                              // merge the 4 lanes of the quad (same row, different keys)
         const float mo = __shfl_xor_sync(0xffffffffu, m[r], o), lo_ = __shfl_xor_sync(0xffffffffu, l[r], o);
         const float mn = fmaxf(m[r], mo);
-        l[r] = (m[r] > -INFINITY ? l[r] * __expf(m[r] - mn) : 0.f) + (mo > -INFINITY ? lo_ * __expf(mo - mn) : 0.f);
+        l[r] = (m[r] > -INFINITY ? l[r] * ex2f(m[r] - mn) : 0.f) + (mo > -INFINITY ? lo_ * ex2f(mo - mn) : 0.f);
         m[r] = mn;
       }
       const int row = qr0 + g + 8 * r;
-      if (tq == 0 && row < a.N) a.lse[(size_t)row * heads + h] = m[r] + logf(l[r]);
+      if (tq == 0 && row < a.N) a.lse[(size_t)row * heads + h] = (m[r] + log2f(l[r])) * 0.6931471805599453f;      // natural log units
     }
     if (t < MT && q0 + t < a.N) {
       const float* o = a.O + (size_t)(q0 + t) * a.ldo + h * BHD;
@@ -574,7 +601,7 @@ __global__ void __launch_bounds__(128) attn_bwd_q_tc_kernel(const AttnBwdArgs a,
 
 extern "C" int dgdm_spatial_attention_backward_tc(const float* qkv, int ld, const float* pos, const int* seg_of, const int* seg_ptr,
                                                   int N, int D, int heads, float temperature, const float* O, int ldo,
-                                                  const float* dO, int lddo, const float* go_scale, float* lse, float* delta,
+                                                  const float* dO, int lddo, const float* go_scale, int have_lse, float* lse, float* delta,
                                                   float* dqkv, int ldd, void* stream) {
   if (!qkv || !seg_of || !seg_ptr || !O || !dO || !go_scale || !lse || !delta || !dqkv) return DGDM_ERR_INVALID;
   if (heads <= 0 || D != heads * BHD || !(temperature > 0.f) || (ld % 4) || (ldo % 4) || (lddo % 4) || (ldd % 2)) return DGDM_ERR_INVALID;
@@ -585,7 +612,8 @@ extern "C" int dgdm_spatial_attention_backward_tc(const float* qkv, int ld, cons
   a.O = O; a.ldo = ldo; a.dO = dO; a.lddo = lddo; a.lse = lse; a.delta = delta; a.dqkv = dqkv; a.ldd = ldd;
   const dim3 grid((N + MT - 1) / MT, heads);
   cudaStream_t s = (cudaStream_t)stream;
-  attn_bwd_q_tc_kernel<0><<<grid, 128, 0, s>>>(a, go_scale);
+  if (have_lse) attn_bwd_delta_kernel<<<(unsigned)(((size_t)N * heads + 255) / 256), 256, 0, s>>>(O, ldo, dO, lddo, N, heads, delta);
+  else attn_bwd_q_tc_kernel<0><<<grid, 128, 0, s>>>(a, go_scale);
   attn_bwd_dkdv_tc_kernel<<<grid, 128, 0, s>>>(a, go_scale);
   attn_bwd_q_tc_kernel<1><<<grid, 128, 0, s>>>(a, go_scale);
   DGDM_CHECK_LAUNCH();

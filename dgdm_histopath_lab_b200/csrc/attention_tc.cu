@@ -819,11 +819,12 @@ size_t attn_tc_work_bytes(int Nq, int Nkv, int D, int heads, int num_seg, int ma
 
 // defined in attention.cu
 void attn_launch_combine(const float* Opart, const float* Mpart, const float* Lpart, int nsplit, int Nq, int D, int heads,
-                         float* out, int ldo, cudaStream_t s);
+                         float* out, int ldo, float* lse_out, cudaStream_t s);
 
 int attn_tc_launch(const float* q_qkv, int ld_q, const float* q_pos, const int* qseg_ptr, int Nq,
                    const float* kv_qkv, int ld_kv, const float* kv_pos, const int* kseg_ptr, int Nkv,
-                   int num_seg, int max_seg_keys, float temperature, float* out, int ldo, void* work, size_t work_bytes, cudaStream_t s) {
+                   int num_seg, int max_seg_keys, float temperature, float* out, int ldo, float* lse_out, void* work, size_t work_bytes,
+                   cudaStream_t s) {
   constexpr int D = 128, heads = 8;
   if (work_bytes < attn_tc_work_bytes(Nq, Nkv, D, heads, num_seg, max_seg_keys)) return DGDM_ERR_INVALID;
   const int ns = attn_tc_nsplit(Nq, Nkv, num_seg, max_seg_keys);
@@ -854,7 +855,7 @@ int attn_tc_launch(const float* q_qkv, int ld_q, const float* q_pos, const int* 
   const int tiles = (Nq + TC_QT - 1) / TC_QT + num_seg;
   if (variant == 8) spatial_attn_tc_kernel<<<dim3(tiles, ns, 1), TC_THREADS, TC_SMEM, s>>>(p);
   else spatial_attn_tc16_kernel<<<dim3(tiles, ns, 1), T16_THREADS, T16_SMEM, s>>>(p);
-  attn_launch_combine(Opart, Mpart, Lpart, ns, Nq, D, heads, out, ldo, s);
+  attn_launch_combine(Opart, Mpart, Lpart, ns, Nq, D, heads, out, ldo, lse_out, s);
   if (cudaGetLastError() != cudaSuccess) return DGDM_ERR_LAUNCH;
   return DGDM_OK;
 }

@@ -318,7 +318,7 @@ def attention_precise_default():
 
 
 def spatial_attention(qkv, pos, seg_ptr, num_seg, heads, temperature=1.0, *, kv_qkv=None, kv_pos=None, kseg_ptr=None,
-                      precise=None, max_seg=0):
+                      precise=None, max_seg=0, want_lse=False):
     """Flash-style attention core. qkv [N, 3D] (q|k|v). pos may be None (no spatial bias). Returns [N, D].
     max_seg: number of keys of the largest segment when known on the host (0 = unknown)."""
     lib = _lib.load()
@@ -333,6 +333,13 @@ def spatial_attention(qkv, pos, seg_ptr, num_seg, heads, temperature=1.0, *, kv_
     wb = int(lib.dgdm_spatial_attention_work_bytes(Nq, Nkv, D, heads, num_seg, max_seg))
     work = torch.empty(wb, dtype=torch.uint8, device=qkv.device)
     out = torch.empty(Nq, D, dtype=torch.float32, device=qkv.device)
+    if want_lse:            # training path: keep the softmax statistics for the backward ([Nq, heads], natural-log units)
+        lse = torch.empty(Nq, heads, dtype=torch.float32, device=qkv.device)
+        _check(lib.dgdm_spatial_attention_lse(_p(_f32c(qkv)), qkv.stride(0), _p(pos), _p(seg_ptr), Nq, _p(_f32c(kv_qkv)),
+                                              kv_qkv.stride(0), _p(kv_pos), _p(kseg_ptr), Nkv, num_seg, max_seg, D, heads,
+                                              float(temperature), precise, _p(out), out.stride(0), _p(lse), _p(work), wb, _stream()),
+               "dgdm_spatial_attention")
+        return out, lse
     _check(lib.dgdm_spatial_attention(_p(_f32c(qkv)), qkv.stride(0), _p(pos), _p(seg_ptr), Nq, _p(_f32c(kv_qkv)),
                                       kv_qkv.stride(0), _p(kv_pos), _p(kseg_ptr), Nkv, num_seg, max_seg, D, heads,
                                       float(temperature), precise, _p(out), out.stride(0), _p(work), wb, _stream()),
@@ -378,7 +385,7 @@ def attention_backward_mode():
     return os.environ.get("DGDM_ATTN_BWD", "tc")
 
 
-def spatial_attention_backward(qkv, pos, seg_of, seg_ptr, heads, temperature, out, grad_out, mode=None):
+def spatial_attention_backward(qkv, pos, seg_of, seg_ptr, heads, temperature, out, grad_out, mode=None, lse=None):
     """d(qkv) of the spatial self-attention core (training path). qkv [N, 3D], out / grad_out [N, D]; seg_of int32 [N].
     mode "tc" (default): mma.sync tensor-core passes, fp16 operands (~2e-3); "simt": exact fp32 CUDA-core passes."""
     lib = _lib.load()
@@ -386,18 +393,20 @@ def spatial_attention_backward(qkv, pos, seg_of, seg_ptr, heads, temperature, ou
     N, D3 = qkv.shape
     D = D3 // 3
     dqkv = torch.empty(N, D3, dtype=torch.float32, device=qkv.device)
-    lse = torch.empty(N, heads, dtype=torch.float32, device=qkv.device)
+    have_lse = int(lse is not None)
+    if lse is None:
+        lse = torch.empty(N, heads, dtype=torch.float32, device=qkv.device)
     delta = torch.empty(N, heads, dtype=torch.float32, device=qkv.device)
     go = _f32c(grad_out.contiguous())
     if mode == "tc":
         sc = torch.exp2(torch.round(torch.log2(8.0 / go.abs().amax().clamp_min(1e-30)))).reshape(1).contiguous()
         _check(lib.dgdm_spatial_attention_backward_tc(_p(_f32c(qkv)), qkv.stride(0), _p(pos), _p(seg_of), _p(seg_ptr), N, D, heads,
                                                       float(temperature), _p(_f32c(out)), out.stride(0), _p(go), go.stride(0), _p(sc),
-                                                      _p(lse), _p(delta), _p(dqkv), dqkv.stride(0), _stream()),
+                                                      have_lse, _p(lse), _p(delta), _p(dqkv), dqkv.stride(0), _stream()),
                "dgdm_spatial_attention_backward_tc")
         return dqkv
     _check(lib.dgdm_spatial_attention_backward(_p(_f32c(qkv)), qkv.stride(0), _p(pos), _p(seg_of), _p(seg_ptr), N, D, heads,
-                                               float(temperature), _p(_f32c(out)), out.stride(0), _p(go), go.stride(0), _p(lse),
+                                               float(temperature), _p(_f32c(out)), out.stride(0), _p(go), go.stride(0), have_lse, _p(lse),
                                                _p(delta), _p(dqkv), dqkv.stride(0), _stream()), "dgdm_spatial_attention_backward")
     return dqkv
 

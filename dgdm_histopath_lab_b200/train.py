@@ -103,16 +103,17 @@ class _SpatialAttnFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, pos, seg_ptr, seg_of, num_seg, heads, temperature, max_seg):
         qkv = qkv.contiguous()
-        out = ops.spatial_attention(qkv, pos, seg_ptr, num_seg, heads, temperature, max_seg=max_seg)
-        ctx.save_for_backward(qkv, out)
+        out, lse = ops.spatial_attention(qkv, pos, seg_ptr, num_seg, heads, temperature, max_seg=max_seg, want_lse=True)
+        ctx.save_for_backward(qkv, out, lse)
         ctx.args = (pos, seg_ptr, seg_of, heads, temperature)
         return out
 
     @staticmethod
     def backward(ctx, go):
-        qkv, out = ctx.saved_tensors
+        qkv, out, lse = ctx.saved_tensors
         pos, seg_ptr, seg_of, heads, temperature = ctx.args
-        return ops.spatial_attention_backward(qkv, pos, seg_of, seg_ptr, heads, temperature, out, go), None, None, None, None, None, None, None
+        return (ops.spatial_attention_backward(qkv, pos, seg_of, seg_ptr, heads, temperature, out, go, lse=lse),
+                None, None, None, None, None, None, None)
 
 
 # ------------------------------------------------------------------------------------------------ layers

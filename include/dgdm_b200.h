@@ -160,6 +160,12 @@ int dgdm_spatial_attention(const float* q_qkv, int ld_q, const float* q_pos, con
                            const float* kv_qkv, int ld_kv, const float* kv_pos, const int* kseg_ptr, int Nkv,
                            int num_seg, int max_seg_keys, int D, int heads, float temperature, int precise,
                            float* out, int ldo, void* work, size_t work_bytes, void* stream);
+/* Same, additionally writing the log-sum-exp of every row's scores per head (natural-log units, [Nq, heads]) for the backward pass.
+ * head_dim 16 only (lse_out must be NULL for the CUDA-core path). */
+int dgdm_spatial_attention_lse(const float* q_qkv, int ld_q, const float* q_pos, const int* qseg_ptr, int Nq,
+                               const float* kv_qkv, int ld_kv, const float* kv_pos, const int* kseg_ptr, int Nkv,
+                               int num_seg, int max_seg_keys, int D, int heads, float temperature, int precise,
+                               float* out, int ldo, float* lse_out, void* work, size_t work_bytes, void* stream);
 /* Head-averaged attention weights [n,n] of ONE graph segment (return_attention=True; O(n^2) output). */
 int dgdm_spatial_attention_weights(const float* qkv, int ld, const float* pos, int n, int D, int heads,
                                    float temperature, float* weights /*[n,n]*/, void* stream);
@@ -181,12 +187,13 @@ int dgdm_mha_dense(const float* q, int ldq, const float* k, int ldk, const float
 
 /* Backward of dgdm_spatial_attention for the training step (models/dgdm_model.py:447-480 runs this layer under
  * autograd): given qkv [N,3D], positions, the forward output O and its gradient dO, returns dqkv [N,3D] (dq | dk | dv).
- * Self-attention inside each graph segment (seg_of[i] = segment of row i, seg_ptr = segment bounds). lse / delta: [N, heads] scratch
- * (log-sum-exp of the scores and O.dO per row and head, recomputed here — the forward keeps no softmax statistics).
+ * Self-attention inside each graph segment (seg_of[i] = segment of row i, seg_ptr = segment bounds). lse / delta: [N, heads]
+ * (log-sum-exp of the scores and O.dO per row and head). have_lse = 1: lse holds the forward's statistics
+ * (dgdm_spatial_attention_lse) and only delta is formed; 0: a recompute pass produces both.
  * head_dim 16 only (DGDM-Base). Exact fp32, deterministic (no atomics). */
 int dgdm_spatial_attention_backward(const float* qkv, int ld, const float* pos, const int* seg_of, const int* seg_ptr,
                                     int N, int D, int heads, float temperature, const float* O, int ldo,
-                                    const float* dO, int lddo, float* lse, float* delta, float* dqkv, int ldd,
+                                    const float* dO, int lddo, int have_lse, float* lse, float* delta, float* dqkv, int ldd,
                                     void* stream);
 
 /* Tensor-core version of the same three passes (warp-level mma.sync m16n8k16, single fp16 operand planes, fp32 accumulation; the
@@ -195,7 +202,7 @@ int dgdm_spatial_attention_backward(const float* qkv, int ld, const float* pos, 
  * tensor-core tolerance), deterministic. */
 int dgdm_spatial_attention_backward_tc(const float* qkv, int ld, const float* pos, const int* seg_of, const int* seg_ptr,
                                        int N, int D, int heads, float temperature, const float* O, int ldo,
-                                       const float* dO, int lddo, const float* go_scale, float* lse, float* delta,
+                                       const float* dO, int lddo, const float* go_scale, int have_lse, float* lse, float* delta,
                                        float* dqkv, int ldd, void* stream);
 
 /* GlobalAttentionPool (models/dgdm_model.py:588-615): one query (q_tok = q_proj(global_token), [D]) per graph

@@ -14,14 +14,14 @@ pos = torch.rand(n, 2, generator=g).cuda()
 go = torch.randn(n, 128, generator=g).cuda()
 seg = torch.tensor([0, n], dtype=torch.int32, device="cuda")
 seg_of = torch.zeros(n, dtype=torch.int32, device="cuda")
-o = ops.spatial_attention(qkv, pos, seg, 1, 8)
-ops.spatial_attention_backward(qkv, pos, seg_of, seg, 8, 1.0, o, go)
+o, lse = ops.spatial_attention(qkv, pos, seg, 1, 8, want_lse=True)
+ops.spatial_attention_backward(qkv, pos, seg_of, seg, 8, 1.0, o, go, lse=lse)
 torch.cuda.synchronize()
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
 ev[0].record()
-o = ops.spatial_attention(qkv, pos, seg, 1, 8)
+o, lse = ops.spatial_attention(qkv, pos, seg, 1, 8, want_lse=True)
 ev[1].record()
-d = ops.spatial_attention_backward(qkv, pos, seg_of, seg, 8, 1.0, o, go)
+d = ops.spatial_attention_backward(qkv, pos, seg_of, seg, 8, 1.0, o, go, lse=lse)
 ev[2].record()
 torch.cuda.synchronize()
 fw, bw = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])

@@ -16,6 +16,7 @@ seg = torch.tensor([0, n], dtype=torch.int32, device="cuda")
 seg_of = torch.zeros(n, dtype=torch.int32, device="cuda")
 o, lse = ops.spatial_attention(qkv, pos, seg, 1, 8, want_lse=True)
 ops.spatial_attention_backward(qkv, pos, seg_of, seg, 8, 1.0, o, go, lse=lse)
+o, lse = ops.spatial_attention(qkv, pos, seg, 1, 8, want_lse=True)
 torch.cuda.synchronize()
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
 ev[0].record()

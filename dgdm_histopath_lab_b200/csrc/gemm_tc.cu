@@ -144,6 +144,31 @@ __device__ __forceinline__ void warp_load_tile(float* st, float* v, const float*
   __syncwarp();
 }
 
+// Split form of warp_load_tile for software pipelining: the global loads of the NEXT 32-column chunk of a residual are issued into
+// registers right after the current chunk was consumed, so their DRAM latency overlaps the epilogue arithmetic instead of sitting in
+// front of the shared-memory transpose (ncu r02e: 98 % long-scoreboard stalls on that store, ~1/4 of the epilogue warps' time).
+__device__ __forceinline__ void warp_load_issue(float4 r[8], const float* G, int ldg, int row0, int c0, int M, int N, int lane) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + (lane >> 3), c = (lane & 7) * 4;
+    r[it] = (row0 + rr < M && c0 + c < N) ? ldg4(G + (size_t)(row0 + rr) * ldg + c0 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+__device__ __forceinline__ void warp_load_commit(float* st, float* v, const float4 r[8], int lane) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + (lane >> 3), c = (lane & 7) * 4;
+    *reinterpret_cast<float4*>(st + rr * TR_STRIDE + c) = r[it];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 t = *reinterpret_cast<const float4*>(st + lane * TR_STRIDE + j * 4);
+    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+  }
+  __syncwarp();
+}
+
 // Column vectors of the epilogue staged once per CTA in shared memory (zero / one filled when absent) so that the element
 // loops below are branch-free FFMA chains fed by broadcast LDS.128 instead of per-element predicated global loads.
 struct EpiVec { const float* bias; const float* g1; const float* b1; const float* g2; const float* b2; const float* dotw; };
@@ -166,12 +191,14 @@ __device__ __forceinline__ void epilogue_rows(const dgdm_gemm_params& p, const E
   const bool writeback = has_ln1 || has_ln2;
   const float invN = 1.0f / (float)p.N;
   float v[32], t[32];
+  float4 pre[8];                // prefetched residual chunk (r_pre in pass 1, r_post in the finishing pass)
   float sum = 0.f, dot = 0.f;
 
   auto finish = [&](int c0) {   // v holds the post-LN values of columns [c0, c0+32)
     apply_act_chunk<32>(v, p.act_post);
     if (p.r_post != nullptr) {
-      warp_load_tile(st, t, p.r_post, p.ld_r_post, row0, c0, p.M, p.N, lane);
+      warp_load_commit(st, t, pre, lane);
+      if (c0 + 32 < p.N) warp_load_issue(pre, p.r_post, p.ld_r_post, row0, c0 + 32, p.M, p.N, lane);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] += t[j];
     }
@@ -205,6 +232,7 @@ __device__ __forceinline__ void epilogue_rows(const dgdm_gemm_params& p, const E
   };
 
   // pass 1: v = acc/scale + bias (+row_bias) (+r_pre); act_pre
+  if (p.r_pre != nullptr) warp_load_issue(pre, p.r_pre, p.ld_r_pre, row0, 0, p.M, p.N, lane);
   for (int c0 = 0; c0 < p.N; c0 += 32) {
     tmem_ld32(t_row + (uint32_t)c0, v);
     if (p.bias != nullptr) {
@@ -228,7 +256,8 @@ __device__ __forceinline__ void epilogue_rows(const dgdm_gemm_params& p, const E
       }
     }
     if (p.r_pre != nullptr) {
-      warp_load_tile(st, t, p.r_pre, p.ld_r_pre, row0, c0, p.M, p.N, lane);
+      warp_load_commit(st, t, pre, lane);
+      if (c0 + 32 < p.N) warp_load_issue(pre, p.r_pre, p.ld_r_pre, row0, c0 + 32, p.M, p.N, lane);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] += t[j];
     }
@@ -241,7 +270,12 @@ __device__ __forceinline__ void epilogue_rows(const dgdm_gemm_params& p, const E
 #pragma unroll
       for (int j = 0; j < 32; ++j) sum += v[j];
       tmem_st32(t_row + (uint32_t)c0, v);
-    } else finish(c0);
+    } else {
+      // r_pre and r_post together without LayerNorm do not occur in the model; keep it correct with an unpipelined load
+      if (p.r_post != nullptr && (c0 == 0 || p.r_pre != nullptr)) warp_load_issue(pre, p.r_post, p.ld_r_post, row0, c0, p.M, p.N, lane);
+      finish(c0);
+      if (p.r_post != nullptr && p.r_pre != nullptr && c0 + 32 < p.N) warp_load_issue(pre, p.r_pre, p.ld_r_pre, row0, c0 + 32, p.M, p.N, lane);
+    }
   }
   if (writeback) {
     const float* g = has_ln1 ? ev.g1 : ev.g2;
@@ -269,6 +303,7 @@ __device__ __forceinline__ void epilogue_rows(const dgdm_gemm_params& p, const E
       rstd = rsqrtf(ss * invN + p.ln_eps);
       g = ev.g2; b = ev.b2;
     }
+    if (p.r_post != nullptr) warp_load_issue(pre, p.r_post, p.ld_r_post, row0, 0, p.M, p.N, lane);
     for (int c0 = 0; c0 < p.N; c0 += 32) {
       tmem_ld32(t_row + (uint32_t)c0, v);
       normalise(c0, g, b, mean, rstd);

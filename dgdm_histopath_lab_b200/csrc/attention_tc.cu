@@ -94,6 +94,22 @@ __device__ __forceinline__ unsigned long long tc_ex2_poly2(unsigned long long x)
 // 216 registers each), so trading one MUFU op for ~6 FMA/ALU issue slots loses; the default therefore stays 0.
 #define TC_POLY_EVERY 0
 #endif
+__device__ __forceinline__ float tc_ex2v(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#ifndef T2_DIST
+#define T2_DIST 8
+#endif
+#ifndef T2_ROLL
+#define T2_ROLL 0          // 1: the 4 heads of a block are a rolled loop (4x less code in the hot loop)
+#endif
+#ifndef T2_EARLY_LD
+#define T2_EARLY_LD 0     // measured: issuing the next TMEM read before the store wait is slower (36.1 vs 35.4 ms)
+#endif
+#ifndef T2_LATE_S
+#define T2_LATE_S 1
+#endif
+#ifndef T2_ABL
+#define T2_ABL 0           // timing ablations (WRONG results): 1 no exp2, 2 pass-through softmax, 3 no distance
+#endif
 __device__ __forceinline__ float tc_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ uint32_t tc_pack_h2(float a, float b) {       // a -> low half, b -> high half
   uint32_t r; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a)); return r;
@@ -473,6 +489,483 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc_kernel(const At
 }
 
 
+// ---------------------------------------------------------------------------------------------- v2: leaner softmax instruction stream
+// Same work decomposition, data images and 3-term split arithmetic as spatial_attn_tc_kernel; what changes is WHERE three pieces of
+// per-score arithmetic run. ncu / tools/mufu_probe.cu showed the softmax warps bound by their instruction stream (10 instructions per
+// two scores around 2 MUFU.EX2), not by the XU pipe alone, while the tensor pipe idles at < 20 %. v2 moves work onto the tensor pipe:
+//   * the reference maximum:  S = Q_h K_h^T - m_h.  A fourth MMA per unit multiplies a [128 x 16] "extension" A tile, whose columns
+//     4i..4i+2 hold -m of head i as three fp16 pieces (exact to 2^-33), with a constant 0/1 B tile that selects head i's columns for
+//     all 64 keys. The softmax thread rewrites its pieces only when its lazy reference changes (first block, then rarely), so the
+//     common path no longer subtracts m per score;
+//   * the row sum:  l_h = P_h 1.  Eight more N = 16 MMAs per unit multiply the P planes (hi, lo) with an all-ones B tile into a
+//     16-column accumulator per head — the same quantised P the numerator uses, no per-score add;
+//   * the distance is kept positive and subtracted (the negation folds into the packed add).
+// Per two scores: 1 FADD2, 2 MUFU.EX2, 2 LOP3, 1 FFMA2, 2 F2FP (8 instead of 10). TMEM (512 columns): 4 S/P slots x 64 | O 8 x 16 |
+// l 8 x 16; Q therefore moves from TMEM to shared memory (SS-mode MMAs; fp16 hi/lo planes in the SWIZZLE_128B layout of the K tiles)
+// and the K/V ring shrinks to 2 stages (measured equal to 3 in round 2). Shared memory: ring 130 KB | Q 64 KB | extension 16 KB |
+// selector 8 KB | ones 2 KB.
+constexpr int T2_STAGES = 2;
+constexpr int T2_OFF_Q = T2_STAGES * TC_IMG;            // [plane 2][group 2][128 rows x 128 B]
+constexpr int T2_OFF_EXT = T2_OFF_Q + 65536;            // [128 rows x 128 B]; group g uses the 16-column K slice g
+constexpr int T2_OFF_SEL = T2_OFF_EXT + 16384;          // [64 keys x 128 B]; K slice i selects head i's extension columns
+constexpr int T2_OFF_ONES = T2_OFF_SEL + 8192;          // [16 x 128 B] of 1.0
+constexpr int T2_OFF_BARS = T2_OFF_ONES + 2048;
+constexpr int T2_SMEM = T2_OFF_BARS + 256 + 1024;
+__device__ __forceinline__ constexpr uint32_t t2_lcol(int h) { return (uint32_t)(384 + 16 * h); }
+
+#ifndef T2_PROF
+#define T2_PROF 0          // 1: cycle accounting of one softmax warp and one MMA issuer of CTA (5, 1) into g_t2_prof (dev builds only)
+#endif
+#if T2_PROF
+__device__ long long g_t2_prof[32];
+#define T2_TICK(idx) do { if (prof_on) { const long long t__ = clock64(); pc[idx] += t__ - tprev; tprev = t__; } } while (0)
+#else
+#define T2_TICK(idx) do { } while (0)
+#endif
+__global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc2_kernel(const AttnTcParams p) {
+  using namespace tc;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* bp = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bars = base + T2_OFF_BARS;
+  // barrier map (8 B each): full[2] @0, empty[2] @24, S_ready[g][s] @48, P_ready[g][s] @80, O_done[g] @112, Q_ready[g] @128
+  const uint32_t bar_full = bars, bar_empty = bars + 24, bar_S = bars + 48, bar_P = bars + 80, bar_O = bars + 112, bar_Q = bars + 128;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bp + T2_OFF_BARS + 192);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int seg = -1, row0 = 0;
+  {
+    int acc = 0;
+    for (int s = 0; s < p.num_seg; ++s) {
+      const int a = p.qseg[s], b = p.qseg[s + 1];
+      const int nt = (b - a + TC_QT - 1) / TC_QT;
+      if ((int)blockIdx.x < acc + nt) { seg = s; row0 = a + ((int)blockIdx.x - acc) * TC_QT; break; }
+      acc += nt;
+    }
+  }
+  if (seg < 0) return;
+  const int qend = p.qseg[seg + 1];
+  const int split = blockIdx.y;
+  const int nb_seg = p.blk_ptr[seg + 1] - p.blk_ptr[seg];
+  const int per = (nb_seg + p.nsplit - 1) / p.nsplit;
+  const int b_lo = min(nb_seg, split * per), b_hi = min(nb_seg, b_lo + per);
+  const int nblk = b_hi - b_lo;
+  const uint8_t* img0 = p.img + (size_t)(p.blk_ptr[seg] + b_lo) * TC_IMG;
+
+  if (tid == 0) {
+    for (int i = 0; i < T2_STAGES; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 2 + 8); }
+    for (int i = 0; i < 4; ++i) { mbar_init(bar_S + 8 * i, 1); mbar_init(bar_P + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_O + 8 * i, 1); mbar_init(bar_Q + 8 * i, 4); }
+    mbar_fence_init();
+  }
+  // constant B tiles: selector (element [key, 16 i + c] = 1 iff c / 4 == i and c % 4 < 3) and ones
+  for (int idx = tid; idx < 64 * 8; idx += TC_THREADS) {
+    const int k = idx >> 3, ch = idx & 7;                         // 16-byte chunk ch = columns 8 ch .. 8 ch + 7
+    uint32_t w[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int c0 = 8 * ch + 2 * t, c1 = c0 + 1;
+      const uint32_t v0 = ((((c0 & 15) >> 2) == (c0 >> 4)) && ((c0 & 3) < 3)) ? 0x3C00u : 0u;
+      const uint32_t v1 = ((((c1 & 15) >> 2) == (c1 >> 4)) && ((c1 & 3) < 3)) ? 0x3C00u : 0u;
+      w[t] = v0 | (v1 << 16);
+    }
+    *reinterpret_cast<uint4*>(bp + T2_OFF_SEL + sw128_off(k, ch)) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  for (int idx = tid; idx < 2048 / 16; idx += TC_THREADS)
+    *reinterpret_cast<uint4*>(bp + T2_OFF_ONES + 16 * idx) = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+  fence_async_smem();
+  if (warp == 10) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tm = *tmem_slot;
+
+  if (warp < 8) {
+    // =========================================================================== softmax groups
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    const int g = warp >> 2, wq = warp & 3;
+    const int rl = wq * 32 + lane;
+    const int row = row0 + rl;
+    const bool rvalid = row < qend;
+    const uint32_t trow = tm + ((uint32_t)(wq * 32) << 16);
+    uint8_t* ext_row = bp + T2_OFF_EXT;                          // this row's extension chunks: 2 g (heads 0, 1), 2 g + 1 (heads 2, 3)
+    float qn[4];
+    // ---- Q: fp32 row -> scaled -> fp16 hi/lo planes in shared memory (A operand of QK^T), |q_h| for the lazy-max bound
+    {
+      const float* qp = p.q_qkv + (size_t)(rvalid ? row : row0) * p.ld_q + 64 * g;
+      uint8_t* qhi = bp + T2_OFF_Q + g * 16384;
+      uint8_t* qlo = qhi + 32768;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t qh[8], ql[8];
+        float sq = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float4 v = ldg4(qp + 16 * i + 4 * c);
+          if (!rvalid) v = make_float4(0.f, 0.f, 0.f, 0.f);
+          v.x *= p.qscale; v.y *= p.qscale; v.z *= p.qscale; v.w *= p.qscale;
+          sq += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+          split_pack(v.x, v.y, qh[2 * c], ql[2 * c]);
+          split_pack(v.z, v.w, qh[2 * c + 1], ql[2 * c + 1]);
+        }
+        qn[i] = sqrtf(sq) * 1.0001f;
+        *reinterpret_cast<uint4*>(qhi + sw128_off(rl, 2 * i)) = make_uint4(qh[0], qh[1], qh[2], qh[3]);
+        *reinterpret_cast<uint4*>(qhi + sw128_off(rl, 2 * i + 1)) = make_uint4(qh[4], qh[5], qh[6], qh[7]);
+        *reinterpret_cast<uint4*>(qlo + sw128_off(rl, 2 * i)) = make_uint4(ql[0], ql[1], ql[2], ql[3]);
+        *reinterpret_cast<uint4*>(qlo + sw128_off(rl, 2 * i + 1)) = make_uint4(ql[4], ql[5], ql[6], ql[7]);
+      }
+      *reinterpret_cast<uint4*>(ext_row + sw128_off(rl, 2 * g)) = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(ext_row + sw128_off(rl, 2 * g + 1)) = make_uint4(0u, 0u, 0u, 0u);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_Q + 8 * g);
+    }
+    float qx = 0.f, qy = 0.f;
+    if (p.q_pos != nullptr && rvalid) { qx = p.q_pos[2 * (size_t)row] * p.pscale; qy = p.q_pos[2 * (size_t)row + 1] * p.pscale; }
+    const unsigned long long qx2 = pk2(qx, qx), qy2 = pk2(qy, qy);
+
+    float m[4];                                                   // reference maximum folded into S from the head's NEXT unit on
+#pragma unroll
+    for (int i = 0; i < 4; ++i) m[i] = -INFINITY;
+
+    uint32_t ra[32], rb[32];
+    const int total = 4 * nblk;
+    if (nblk > 0) {
+      mbar_wait_parked(bar_S + 8 * (2 * g), 0);
+      fence_after();
+      tmem_ld32_nowait(trow + tc_slot(g, 0), ra);
+      tmem_ld32_nowait(trow + tc_slot(g, 0) + 32, rb);
+    }
+    const unsigned long long neg1 = pk2(-1.0f, -1.0f);
+    // exp2 + fp16 hi/lo split of one 32-key chunk held in r (in place); r already carries q.k - m, dc the (scaled) distances.
+    // Software-pipelined by hand: the MUFU.EX2 of pair t + T2_DIST is issued before pair t is split, so that a result is consumed
+    // ~T2_DIST x 16 XU cycles after its issue (ptxas otherwise schedules the dependent LOP3 a few slots behind its MUFU and the
+    // in-order warp stalls on the scoreboard while the XU queue drains).
+    auto softmax_chunk = [&](uint32_t* r, const unsigned long long* dc) {
+      constexpr int D = T2_DIST;
+      float pv[32];
+      auto ex = [&](int t) {                                      // pair t = elements (2t, 2t+1) of the chunk
+        const unsigned long long x = sub2(pk2(__uint_as_float(r[2 * t]), __uint_as_float(r[2 * t + 1])), dc[t]);
+#if T2_ABL == 1
+        pv[2 * t] = lo32(x); pv[2 * t + 1] = hi32(x);
+#else
+        pv[2 * t] = tc_ex2v(lo32(x)); pv[2 * t + 1] = tc_ex2v(hi32(x));
+#endif
+      };
+#if T2_ABL == 2 || T2_ABL == 4
+      if (dc != nullptr) return;
+#endif
+      uint32_t hi[16], lo[16];
+      auto sp = [&](int t) {
+        const float p0 = pv[2 * t], p1 = pv[2 * t + 1];
+        const float h0 = __uint_as_float(__float_as_uint(p0) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(p1) & 0xffffe000u);
+        const unsigned long long ll = fma2(pk2(h0, h1), neg1, pk2(p0, p1));
+        hi[t] = tc_pack_h2(h0, h1);
+        lo[t] = tc_pack_h2(lo32(ll), hi32(ll));
+      };
+#pragma unroll
+      for (int t = 0; t < D; ++t) ex(t);
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        if (t + D < 16) ex(t + D);
+        sp(t);
+      }
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { r[16 * ks + t] = hi[8 * ks + t]; r[16 * ks + 8 + t] = lo[8 * ks + t]; }
+      }
+    };
+
+#if T2_PROF
+    const bool prof_on = (blockIdx.x == 5 && blockIdx.y == 1 && warp == 0);
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = clock64();
+    const long long tstart = tprev;
+#endif
+    bool f_ok = false;                                           // early test of the next block's full barrier succeeded
+    for (int j = 0; j < nblk; ++j) {
+      const int st = j % T2_STAGES;
+      if (!f_ok) mbar_wait_parked(bar_full + 8 * st, (uint32_t)((j / T2_STAGES) & 1));
+      f_ok = false;
+      T2_TICK(0);
+      // ---- scaled distance of this row to the block's 64 keys (shared by the group's 4 heads); +inf for padded keys
+      unsigned long long db[32];
+      float kmax[4];
+      {
+        const float* kp = reinterpret_cast<const float*>(bp + st * TC_IMG + TC_OFF_POS);
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          const float4 kx = *reinterpret_cast<const float4*>(kp + 4 * t);
+          const float4 ky = *reinterpret_cast<const float4*>(kp + TC_BN + 4 * t);
+          unsigned long long dx = sub2(qx2, pk2(kx.x, kx.y)), dy = sub2(qy2, pk2(ky.x, ky.y));
+          unsigned long long d2 = fma2(dx, dx, mul2(dy, dy));
+#if T2_ABL == 3 || T2_ABL == 4
+          db[2 * t] = d2;
+#else
+          db[2 * t] = pk2(tc_sqrt(lo32(d2)), tc_sqrt(hi32(d2)));
+#endif
+          dx = sub2(qx2, pk2(kx.z, kx.w)); dy = sub2(qy2, pk2(ky.z, ky.w));
+          d2 = fma2(dx, dx, mul2(dy, dy));
+#if T2_ABL == 3 || T2_ABL == 4
+          db[2 * t + 1] = d2;
+#else
+          db[2 * t + 1] = pk2(tc_sqrt(lo32(d2)), tc_sqrt(hi32(d2)));
+#endif
+        }
+        const float4 km = *reinterpret_cast<const float4*>(bp + st * TC_IMG + TC_OFF_KMAX + 16 * g);
+        kmax[0] = km.x; kmax[1] = km.y; kmax[2] = km.z; kmax[3] = km.w;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_empty + 8 * st);
+      T2_TICK(1);
+
+      float bound[4];                                            // Cauchy-Schwarz bound on q.k of this row against the block, per head
+#pragma unroll
+      for (int i = 0; i < 4; ++i) bound[i] = qn[i] * kmax[i];
+#if T2_ROLL
+#pragma unroll 1
+#else
+#pragma unroll
+#endif
+      for (int i = 0; i < 4; ++i) {
+        const int u = 4 * j + i, s = u & 1;
+        const uint32_t slot = trow + tc_slot(g, s);
+        const uint32_t nslot = trow + tc_slot(g, s ^ 1);
+        // head-indexed state through selects (constant register indices also when the loop is not unrolled)
+        const float m_i = (i == 0) ? m[0] : (i == 1) ? m[1] : (i == 2) ? m[2] : m[3];
+        const float bound_i = (i == 0) ? bound[0] : (i == 1) ? bound[1] : (i == 2) ? bound[2] : bound[3];
+        tmem_wait_ld();
+        T2_TICK(2);
+        // ---- lazy reference: S already carries -m[i] (0 while m[i] = -inf). Only when the Cauchy-Schwarz bound admits an overflow
+        // of the current reference is the block's row maximum looked at; a new reference shifts this unit's scores in registers,
+        // rescales O_h / l_h and is published to the extension tile for the head's following units.
+        const bool need = (m_i == -INFINITY) || (bound_i > m_i + TC_TAU);
+        if (__any_sync(0xffffffffu, need)) {
+          float rmax = -INFINITY;                                 // relative to the folded reference
+#pragma unroll
+          for (int t = 0; t < 16; ++t) {
+            const unsigned long long xa = sub2(pk2(__uint_as_float(ra[2 * t]), __uint_as_float(ra[2 * t + 1])), db[t]);
+            const unsigned long long xb = sub2(pk2(__uint_as_float(rb[2 * t]), __uint_as_float(rb[2 * t + 1])), db[16 + t]);
+            rmax = fmaxf(rmax, fmaxf(fmaxf(lo32(xa), hi32(xa)), fmaxf(lo32(xb), hi32(xb))));
+          }
+          float delta = 0.f, sc = 1.0f, m_new = m_i;
+          if (m_i == -INFINITY) { if (rmax > -INFINITY) { m_new = rmax; delta = -rmax; } }     // everything accumulated so far is 0
+          else if (rmax > TC_TAU) { sc = tc_ex2(-rmax); m_new = m_i + rmax; delta = -rmax; }
+          if (i == 0) m[0] = m_new; else if (i == 1) m[1] = m_new; else if (i == 2) m[2] = m_new; else m[3] = m_new;
+          if (__any_sync(0xffffffffu, sc != 1.0f)) {
+            // every PV / row-sum MMA on head i issued so far has completed (in-order MMA pipe, S_ready of this unit waited)
+            uint32_t o[16];
+            tmem_ld16_nowait(trow + tc_ocol(4 * g + i), o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int t = 0; t < 16; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) * sc);
+            tmem_st16_nowait(trow + tc_ocol(4 * g + i), o);
+            tmem_ld16_nowait(trow + t2_lcol(4 * g + i), o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int t = 0; t < 16; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) * sc);
+            tmem_st16_nowait(trow + t2_lcol(4 * g + i), o);
+          }
+          if (__any_sync(0xffffffffu, delta != 0.f)) {
+            const unsigned long long d2 = pk2(delta, delta);
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+              const unsigned long long xa = add2(pk2(__uint_as_float(ra[2 * t]), __uint_as_float(ra[2 * t + 1])), d2);
+              const unsigned long long xb = add2(pk2(__uint_as_float(rb[2 * t]), __uint_as_float(rb[2 * t + 1])), d2);
+              ra[2 * t] = (uint32_t)xa; ra[2 * t + 1] = (uint32_t)(xa >> 32);
+              rb[2 * t] = (uint32_t)xb; rb[2 * t + 1] = (uint32_t)(xb >> 32);
+            }
+            if (delta != 0.f) {
+              // -m as three fp16 pieces (hi + mid + lo reproduces the fp32 value to 2^-33) in columns 4 i .. 4 i + 2 of the slice
+              const float nm = -m_new;
+              const __half e0 = __float2half_rn(nm);
+              const float r1 = nm - __half2float(e0);
+              const __half e1 = __float2half_rn(r1);
+              const __half e2 = __float2half_rn(r1 - __half2float(e1));
+              const uint32_t w0 = (uint32_t)__half_as_ushort(e0) | ((uint32_t)__half_as_ushort(e1) << 16);
+              const uint32_t w1 = (uint32_t)__half_as_ushort(e2);
+              *reinterpret_cast<uint2*>(ext_row + sw128_off(rl, 2 * g + (i >> 1)) + 8 * (i & 1)) = make_uint2(w0, w1);
+              fence_async_smem();
+            }
+          }
+        }
+        softmax_chunk(ra, db);
+#if T2_LATE_S
+        // A barrier test costs ~180 cycles even when the phase is complete (tools/tc_probe.cu): test S_ready of the next unit and
+        // the next block's full barrier here, one chunk before the results are needed (ahead of the TMEM store, which ptxas does
+        // not move it across), and only park on them if that test failed.
+        bool s_ok = false;
+        if (u + 1 < total) s_ok = mbar_test_wait(bar_S + 8 * (2 * g + (s ^ 1)), (uint32_t)(((u + 1) >> 1) & 1));
+        if (i == 3 && j + 1 < nblk) f_ok = mbar_test_wait(bar_full + 8 * ((j + 1) % T2_STAGES), (uint32_t)(((j + 1) / T2_STAGES) & 1));
+#endif
+        tmem_st32_nowait(slot, ra);
+        T2_TICK(3);
+#if !T2_LATE_S
+        if (u + 1 < total) {
+          mbar_wait_parked(bar_S + 8 * (2 * g + (s ^ 1)), (uint32_t)(((u + 1) >> 1) & 1));
+          fence_after();
+          tmem_ld32_nowait(nslot, ra);
+        }
+#endif
+        T2_TICK(4);
+        softmax_chunk(rb, db + 16);
+        tmem_st32_nowait(slot + 32, rb);
+        T2_TICK(5);
+#if T2_EARLY_LD
+        // second half of the next unit: issued BEFORE the store wait so that the TMEM read latency overlaps it (the store has
+        // captured rb's registers at issue; S of unit u + 1 was waited for above)
+        if (u + 1 < total) tmem_ld32_nowait(nslot + 32, rb);
+#endif
+        tmem_wait_st();
+        fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_P + 8 * (2 * g + s));
+#if T2_LATE_S
+        // S of the next unit is fetched only now: its QK^T MMAs sit behind this group's previous PV / row-sum MMAs and one
+        // barrier round trip (~1000 cycles after P_ready of unit u - 1), so waiting for it in the middle of the unit stalled the
+        // warp for ~350 cycles per unit (cycle accounting, tools/attn_prof.py); here it has long arrived.
+        if (u + 1 < total) {
+          if (!s_ok) mbar_wait_parked(bar_S + 8 * (2 * g + (s ^ 1)), (uint32_t)(((u + 1) >> 1) & 1));
+          fence_after();
+          tmem_ld32_nowait(nslot, ra);
+          tmem_ld32_nowait(nslot + 32, rb);
+        }
+#elif !T2_EARLY_LD
+        if (u + 1 < total) tmem_ld32_nowait(nslot + 32, rb);
+#endif
+        T2_TICK(6);
+      }
+    }
+#if T2_PROF
+    if (prof_on && lane == 0) {
+      for (int q = 0; q < 8; ++q) g_t2_prof[q] = pc[q];
+      g_t2_prof[8] = clock64() - tstart; g_t2_prof[9] = nblk;
+    }
+#endif
+    // ---- epilogue: unnormalised O, reference max m, row sum l of this key split
+    if (nblk > 0) { mbar_wait_parked(bar_O + 8 * g, 0); fence_after(); }
+    const size_t prow = (size_t)split * p.Nq + (size_t)row;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      if (nblk > 0) { tmem_ld32_nowait(trow + tc_ocol(4 * g) + 32 * c, r); tmem_wait_ld(); }
+      else {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) r[t] = 0u;
+      }
+      if (rvalid) {
+        float* op = p.Opart + prow * 128 + 64 * g + 32 * c;
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+          *reinterpret_cast<float4*>(op + 4 * t) = make_float4(__uint_as_float(r[4 * t]), __uint_as_float(r[4 * t + 1]),
+                                                               __uint_as_float(r[4 * t + 2]), __uint_as_float(r[4 * t + 3]));
+      }
+    }
+    {
+      float l[4] = {0.f, 0.f, 0.f, 0.f};
+      if (nblk > 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t r[16];
+          tmem_ld16_nowait(trow + t2_lcol(4 * g + i), r);
+          tmem_wait_ld();
+          l[i] = __uint_as_float(r[0]);
+        }
+      }
+      if (rvalid) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          p.Mpart[prow * 8 + 4 * g + i] = m[i];
+          p.Lpart[prow * 8 + 4 * g + i] = l[i];
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp < 10) {
+    // =========================================================================== MMA issuers (one per head group)
+    const int g = warp - 8;
+    if (nblk > 0 && elect_one()) {
+      const uint32_t id64 = idesc_f16(128, 64), id16 = idesc_f16(128, 16);
+      const int total = 4 * nblk;
+      const uint32_t qh_b = base + T2_OFF_Q + 16384 * g, ql_b = qh_b + 32768;
+      const uint64_t ext_d = desc_sw128(base + T2_OFF_EXT + 32 * g);
+      const uint64_t ones_d = desc_sw128(base + T2_OFF_ONES);
+      TC_ROLE_WAIT(bar_Q + 8 * g, 0);
+      fence_after();
+      auto issue_qk = [&](int u) {
+        const int b = u >> 2, i = u & 3, st = b % T2_STAGES;
+        if (i == 0) { TC_ROLE_WAIT(bar_full + 8 * st, (uint32_t)((b / T2_STAGES) & 1)); fence_after(); }
+        const uint32_t d = tm + tc_slot(g, u & 1);
+        const uint32_t kb = base + st * TC_IMG + 8192 * g + 32 * i;
+        mma_ss(d, desc_sw128(qh_b + 32 * i), desc_sw128(kb), id64, 0);
+        mma_ss(d, desc_sw128(ql_b + 32 * i), desc_sw128(kb), id64, 1);
+        mma_ss(d, desc_sw128(qh_b + 32 * i), desc_sw128(kb + 16384), id64, 1);
+        mma_ss(d, ext_d, desc_sw128(base + T2_OFF_SEL + 32 * i), id64, 1);          // - m_h (0 until the first reference is published)
+        mma_commit(bar_S + 8 * (2 * g + (u & 1)));
+      };
+#if T2_PROF
+      const bool prof_on = (blockIdx.x == 5 && blockIdx.y == 1 && g == 0);
+      long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      long long tprev = clock64();
+      const long long tstart = tprev;
+#endif
+      issue_qk(0);
+      if (total > 1) issue_qk(1);
+      T2_TICK(0);
+      for (int u = 0; u < total; ++u) {
+        const int b = u >> 2, i = u & 3, st = b % T2_STAGES, h = 4 * g + i;
+        TC_ROLE_WAIT(bar_P + 8 * (2 * g + (u & 1)), (uint32_t)((u >> 1) & 1));
+        fence_after();
+        T2_TICK(1);
+        const uint32_t vb = base + st * TC_IMG + TC_OFF_V + 2048 * h;
+        const uint32_t ps = tm + tc_slot(g, u & 1);
+        const uint32_t od = tm + tc_ocol(h), ld = tm + t2_lcol(h);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          mma_ts(od, ps + 16 * ks, desc_sw128(vb + 32 * ks), id16, (b > 0 || ks > 0) ? 1u : 0u);
+          mma_ts(od, ps + 16 * ks + 8, desc_sw128(vb + 32 * ks), id16, 1);
+          mma_ts(od, ps + 16 * ks, desc_sw128(vb + 16384 + 32 * ks), id16, 1);
+          mma_ts(ld, ps + 16 * ks, ones_d, id16, (b > 0 || ks > 0) ? 1u : 0u);       // l_h += rowsum(P hi) + rowsum(P lo)
+          mma_ts(ld, ps + 16 * ks + 8, ones_d, id16, 1);
+        }
+        if (i == 3) mma_commit(bar_empty + 8 * st);
+        T2_TICK(2);
+        if (u + 2 < total) issue_qk(u + 2);
+        T2_TICK(3);
+      }
+      mma_commit(bar_O + 8 * g);
+#if T2_PROF
+      if (prof_on) {
+        for (int q = 0; q < 8; ++q) g_t2_prof[16 + q] = pc[q];
+        g_t2_prof[24] = clock64() - tstart;
+      }
+#endif
+    }
+    __syncwarp();
+    } else if (warp == 10) {
+    // =========================================================================== loader (cp.async.bulk, 2-stage ring)
+    if (elect_one()) {
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j % T2_STAGES;
+        TC_ROLE_WAIT(bar_empty + 8 * st, (uint32_t)(((j / T2_STAGES) & 1) ^ 1));
+        mbar_arrive_expect_tx(bar_full + 8 * st, TC_IMG_USED);
+        const uint8_t* src = img0 + (size_t)j * TC_IMG;
+        const uint32_t dst = base + st * TC_IMG;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) bulk_g2s(dst + 16384 * c, src + 16384 * c, 16384, bar_full + 8 * st);
+        bulk_g2s(dst + 65536, src + 65536, TC_IMG_USED - 65536, bar_full + 8 * st);
+      }
+    }
+    __syncwarp();
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 10) tmem_dealloc(tm, 512);
+}
+
 // ---------------------------------------------------------------------------------------------- 16-softmax-warp variant
 // MEASURED SLOWER than the 8-warp kernel (37.5 vs 35.9 ms at 100k nodes, profiles/attn_tc16_r02b.txt, profiles/microbench_r02.txt) and therefore NOT the default
 // (DGDM_ATTN_TC_WARPS=16 selects it): the kernel is not latency-bound. tools/mufu_probe.cu shows that the softmax instruction mix
@@ -842,10 +1335,12 @@ int attn_tc_launch(const float* q_qkv, int ld_q, const float* q_pos, const int* 
   static PerDeviceOnce attr_set;
   if (attr_set.needed()) {
     if (cudaFuncSetAttribute(spatial_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(spatial_attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(spatial_attn_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T16_SMEM) != cudaSuccess) return DGDM_ERR_LAUNCH;
     attr_set.mark();
   }
-  static const int variant = [] { const char* e = getenv("DGDM_ATTN_TC_WARPS"); return e ? atoi(e) : 8; }();
+  // 2 = spatial_attn_tc2_kernel (default), 8 = the round-1/2 kernel, 16 = its 16-softmax-warp variant
+  static const int variant = [] { const char* e = getenv("DGDM_ATTN_TC_WARPS"); return e ? atoi(e) : 2; }();
   static const int sleep_ns = [] { const char* e = getenv("DGDM_ATTN_TC_SLEEP"); return e ? atoi(e) : 0; }();
   AttnTcParams p;
   p.q_qkv = q_qkv; p.ld_q = ld_q; p.q_pos = q_pos; p.qseg = qseg_ptr; p.kseg = kseg_ptr; p.num_seg = num_seg; p.Nq = Nq; p.nsplit = ns;
@@ -853,7 +1348,8 @@ int attn_tc_launch(const float* q_qkv, int ld_q, const float* q_pos, const int* 
   p.Opart = Opart; p.Mpart = Mpart; p.Lpart = Lpart;
   p.mma_sleep_ns = sleep_ns;
   const int tiles = (Nq + TC_QT - 1) / TC_QT + num_seg;
-  if (variant == 8) spatial_attn_tc_kernel<<<dim3(tiles, ns, 1), TC_THREADS, TC_SMEM, s>>>(p);
+  if (variant == 2) spatial_attn_tc2_kernel<<<dim3(tiles, ns, 1), TC_THREADS, T2_SMEM, s>>>(p);
+  else if (variant == 8) spatial_attn_tc_kernel<<<dim3(tiles, ns, 1), TC_THREADS, TC_SMEM, s>>>(p);
   else spatial_attn_tc16_kernel<<<dim3(tiles, ns, 1), T16_THREADS, T16_SMEM, s>>>(p);
   attn_launch_combine(Opart, Mpart, Lpart, ns, Nq, D, heads, out, ldo, lse_out, s);
   if (cudaGetLastError() != cudaSuccess) return DGDM_ERR_LAUNCH;
@@ -861,3 +1357,9 @@ int attn_tc_launch(const float* q_qkv, int ld_q, const float* q_pos, const int* 
 }
 
 }  // namespace dgdm
+
+#if T2_PROF
+extern "C" int dgdm_debug_attn_prof(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, dgdm::g_t2_prof, sizeof(long long) * 32) == cudaSuccess ? 0 : 1;
+}
+#endif

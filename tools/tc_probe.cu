@@ -163,6 +163,36 @@ __global__ void __launch_bounds__(192, 1) probe_kernel(const __half* Q, const __
     t1 = clock64();
     out->cyc[8] = (t1 - t0) / 64;
   }
+  // ------------------------------------------------------------------ MMA issue under MUFU load (the attention kernel's situation:
+  // the issuing thread shares its scheduler and the MIO queue with exp2-heavy softmax warps)
+  volatile int* stop = reinterpret_cast<volatile int*>(bp + OFF_BAR + 192);
+  if (tid == 0) *stop = 0;
+  fence_before();
+  __syncthreads();
+  fence_after();
+  if (warp < 4) {
+    float x = 0.001f * tid, acc = 0.f;
+    long long n = 0;
+    while (*stop == 0) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x + i * 0.01f)); acc += y; }
+      x = acc * 1e-9f; ++n;
+    }
+    if (acc == 12345.f) out->cyc[15] = n;
+  } else if (warp == 4 && elect_one()) {
+    for (int rep = 0; rep < 2; ++rep) {
+      long long t0 = clock64();
+      for (int i = 0; i < 64; ++i)
+        mma_ts(tm + O_COL, tm + 16 * (i & 3), desc_sw128(base + OFF_V + 32 * (i & 3)), idesc_f16(128, 16), 1);
+      mma_commit(bar + 24);
+      long long t1 = clock64();
+      mbar_wait(bar + 24, rep & 1);
+      long long t2 = clock64();
+      out->cyc[9] = (t1 - t0) / 64;                        // issue cost per TS MMA (N=16) under MUFU load
+      out->cyc[10] = (t2 - t0) / 64;
+    }
+    *stop = 1;
+  }
   fence_before();
   __syncthreads();
   if (warp == 4) tmem_dealloc(tm, 512);
@@ -208,7 +238,8 @@ int main() {
   printf("S  max abs err %.3e (max |S| %.3f)  -> %s\n", eS, mS, eS < 1e-5 * mS ? "OK" : "MISMATCH");
   printf("O  max abs err %.3e (max |O| %.3f)  -> %s\n", eO, mO, eO < 1e-5 * mO ? "OK" : "MISMATCH");
   const char* names[] = {"tmem ld.x32+wait (latency)", "tmem ld.x32 4-deep (per instr)", "tmem st.x32 (per instr)", "TS MMA N=16 issue", "TS MMA N=16 complete",
-                         "SS MMA N=64 issue", "SS MMA N=64 complete", "commit+wait round trip", "mbar wait (complete phase)"};
-  for (int i = 0; i < 9; ++i) printf("cycles  %-34s %lld\n", names[i], o->cyc[i]);
+                         "SS MMA N=64 issue", "SS MMA N=64 complete", "commit+wait round trip", "mbar wait (complete phase)",
+                         "TS MMA N=16 issue, MUFU-loaded SM", "TS MMA N=16 complete, MUFU-loaded"};
+  for (int i = 0; i < 11; ++i) printf("cycles  %-34s %lld\n", names[i], o->cyc[i]);
   return (eS < 1e-5 * mS && eO < 1e-5 * mO) ? 0 : 1;
 }

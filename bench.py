@@ -555,7 +555,7 @@ def main():
     mufu_peak = 148 * 16 * sm_clock_ghz
     large = args.workload == "large"
     ops_per_score = ops.ATTN_MUFU_PER_SCORE                                   # exp2 + the share of the distance sqrt
-    roof = {"kernel": "spatial_attn_tc_kernel (+ prep / combine kernels of the same dgdm_spatial_attention call)"
+    roof = {"kernel": "spatial_attn_tc2_kernel (+ prep / combine kernels of the same dgdm_spatial_attention call)"
                       + ("; DGDM-Large: 16 heads x 8 zero-padded to 16 dims, two 8-head passes" if large else ""),
             "bound": "mufu", "unit": "G MUFU ops/s", "ms": att_ms, "ops_per_score": ops_per_score,
             "achieved": ops_per_score * att_exp / (att_ms * 1e-3) / 1e9 if att_ms else None, "peak": mufu_peak,
@@ -567,7 +567,7 @@ def main():
     roof["frac"] = roof["achieved"] / roof["peak"] if roof["achieved"] else None
     if roof["tensor"]["achieved"]:
         roof["tensor"]["frac"] = roof["tensor"]["achieved"] / roof["tensor"]["peak"]
-    roof["traffic"], roof["traffic_source"] = ncu_traffic("spatial_attn_tc_kernel")
+    roof["traffic"], roof["traffic_source"] = ncu_traffic("spatial_attn_tc2_kernel")
     roof_hbm = {"kernel": "spmm_gcn_kernel (all launches)", "bound": "hbm", "achieved": spmm_bytes / (spmm_ms * 1e-3) / 1e9 if spmm_ms else None,
                 "peak": pk["hbm"], "unit": "GB/s", "ms": spmm_ms, "launches": len(meta.get("spmm", [])),
                 "algorithmic_bytes": spmm_bytes}

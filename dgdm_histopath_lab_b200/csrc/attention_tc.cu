@@ -89,7 +89,8 @@ __device__ __forceinline__ unsigned long long tc_ex2_poly2(unsigned long long x)
   return (unsigned long long)r0 | ((unsigned long long)r1 << 32);
 }
 #ifndef TC_POLY_EVERY
-// Every TC_POLY_EVERY-th element pair takes the polynomial path (0 = never). MEASURED on B200 at 100k nodes (tools/attn_exp.sh):
+// Every TC_POLY_EVERY-th element pair takes the polynomial path (0 = never; T2_POLY is the same knob for the v2 kernel, measured
+// 33.30 ms at 8 and 34.28 ms at 4 vs 33.16 ms at 0). MEASURED on B200 at 100k nodes (tools/attn_exp.sh):
 // 0 -> 35.2 ms, 4 -> 38.5 ms, 3 -> 38.9 ms, 2 -> 43.9 ms: the softmax warps are issue/latency-bound (2 warps per scheduler,
 // 216 registers each), so trading one MUFU op for ~6 FMA/ALU issue slots loses; the default therefore stays 0.
 #define TC_POLY_EVERY 0
@@ -101,11 +102,14 @@ __device__ __forceinline__ float tc_ex2v(float x) { float y; asm volatile("ex2.a
 #ifndef T2_ROLL
 #define T2_ROLL 0          // 1: the 4 heads of a block are a rolled loop (4x less code in the hot loop)
 #endif
-#ifndef T2_EARLY_LD
-#define T2_EARLY_LD 0     // measured: issuing the next TMEM read before the store wait is slower (36.1 vs 35.4 ms)
+#ifndef T2_PIPE
+// 1: chunk-level TMEM pipeline (every read issued one chunk before its wait, P_ready of unit u arrived after the first chunk of
+// unit u + 1). MEASURED SLOWER: 35.8 vs 33.06 ms at 100k nodes (ptxas merges the two chunks into one schedule and sinks the TMEM
+// accesses; with scheduling fences between the chunks it reaches 32.8 ms in the instrumented build) -> the unit-level order stays.
+#define T2_PIPE 0
 #endif
-#ifndef T2_LATE_S
-#define T2_LATE_S 1
+#ifndef T2_POLY
+#define T2_POLY 0
 #endif
 #ifndef T2_ABL
 #define T2_ABL 0           // timing ablations (WRONG results): 1 no exp2, 2 pass-through softmax, 3 no distance
@@ -489,29 +493,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc_kernel(const At
 }
 
 
-// ---------------------------------------------------------------------------------------------- v2: leaner softmax instruction stream
-// Same work decomposition, data images and 3-term split arithmetic as spatial_attn_tc_kernel; what changes is WHERE three pieces of
-// per-score arithmetic run. ncu / tools/mufu_probe.cu showed the softmax warps bound by their instruction stream (10 instructions per
-// two scores around 2 MUFU.EX2), not by the XU pipe alone, while the tensor pipe idles at < 20 %. v2 moves work onto the tensor pipe:
-//   * the reference maximum:  S = Q_h K_h^T - m_h.  A fourth MMA per unit multiplies a [128 x 16] "extension" A tile, whose columns
-//     4i..4i+2 hold -m of head i as three fp16 pieces (exact to 2^-33), with a constant 0/1 B tile that selects head i's columns for
-//     all 64 keys. The softmax thread rewrites its pieces only when its lazy reference changes (first block, then rarely), so the
-//     common path no longer subtracts m per score;
-//   * the row sum:  l_h = P_h 1.  Eight more N = 16 MMAs per unit multiply the P planes (hi, lo) with an all-ones B tile into a
-//     16-column accumulator per head — the same quantised P the numerator uses, no per-score add;
-//   * the distance is kept positive and subtracted (the negation folds into the packed add).
-// Per two scores: 1 FADD2, 2 MUFU.EX2, 2 LOP3, 1 FFMA2, 2 F2FP (8 instead of 10). TMEM (512 columns): 4 S/P slots x 64 | O 8 x 16 |
-// l 8 x 16; Q therefore moves from TMEM to shared memory (SS-mode MMAs; fp16 hi/lo planes in the SWIZZLE_128B layout of the K tiles)
-// and the K/V ring shrinks to 2 stages (measured equal to 3 in round 2). Shared memory: ring 130 KB | Q 64 KB | extension 16 KB |
-// selector 8 KB | ones 2 KB.
+// ---------------------------------------------------------------------------------------------- v2: restructured around measured latencies
+// Same work decomposition, data images and 3-term split arithmetic as spatial_attn_tc_kernel. In-kernel cycle accounting
+// (tools/attn_prof.py) and timing ablations (T2_ABL) showed what the ncu counters could not: the exp2 / split chunks already ran at
+// ~90 % of the XU bound, and the rest of a unit's ~1950 cycles went to (a) ~350 cycles parked on S_ready of the next unit — its
+// QK^T MMAs could only be issued after the PV MMAs that free the in-place P slot, ~1000 cycles after P_ready — and (b) barrier tests
+// that cost ~180 cycles even when the phase is already complete. v2 therefore:
+//   * keeps THREE S/P slots per head group, so QK^T of unit u + 3 is issued right behind PV of unit u and S is ready two units ahead;
+//     the TMEM columns come from moving Q to shared memory (SS-mode MMAs on fp16 hi/lo planes in the SWIZZLE_128B layout of the K
+//     tiles; slower per MMA than TMEM operands, but off the critical path now);
+//   * folds the reference maximum into the MMA:  S = Q_h K_h^T - m_h.  A fourth MMA per unit multiplies a [128 x 16] "extension" A
+//     tile, whose columns 4i..4i+2 hold -m of head i as three fp16 pieces (exact to 2^-33), with a constant 0/1 selector B tile.
+//     The softmax thread rewrites its pieces only when its lazy reference changes (first block, then rarely), so the common path no
+//     longer subtracts m per score; the distance is kept positive and subtracted (the negation folds into the packed add);
+//   * fetches S of the next unit at the END of a unit and tests the barriers one chunk before their results are needed.
+// Per two scores: 2 FADD2, 2 MUFU.EX2, 2 LOP3, 1 FFMA2, 2 F2FP (9 instead of 10). TMEM (512 columns): 6 S/P slots x 64 | O 8 x 16.
+// Shared memory: K/V ring 2 x 65 KB (2 stages measured equal to 3 in round 2) | Q 64 KB | extension 16 KB | selector 8 KB.
+// (A variant that also computed the row sums on the tensor pipe — ones-tile MMAs into 16-column accumulators, 8 instructions per two
+// scores — measured 33.7 ms with two slots; it needs the TMEM columns of the third slot and lengthens the MMA chain, see git history.)
 constexpr int T2_STAGES = 2;
 constexpr int T2_OFF_Q = T2_STAGES * TC_IMG;            // [plane 2][group 2][128 rows x 128 B]
 constexpr int T2_OFF_EXT = T2_OFF_Q + 65536;            // [128 rows x 128 B]; group g uses the 16-column K slice g
 constexpr int T2_OFF_SEL = T2_OFF_EXT + 16384;          // [64 keys x 128 B]; K slice i selects head i's extension columns
-constexpr int T2_OFF_ONES = T2_OFF_SEL + 8192;          // [16 x 128 B] of 1.0
-constexpr int T2_OFF_BARS = T2_OFF_ONES + 2048;
+constexpr int T2_OFF_BARS = T2_OFF_SEL + 8192;
 constexpr int T2_SMEM = T2_OFF_BARS + 256 + 1024;
-__device__ __forceinline__ constexpr uint32_t t2_lcol(int h) { return (uint32_t)(384 + 16 * h); }
+__device__ __forceinline__ uint32_t t2_slot(int g, int k) { return (uint32_t)((3 * g + k) * 64); }     // k = unit % 3
+__device__ __forceinline__ constexpr uint32_t t2_ocol(int h) { return (uint32_t)(384 + 16 * h); }
 
 #ifndef T2_PROF
 #define T2_PROF 0          // 1: cycle accounting of one softmax warp and one MMA issuer of CTA (5, 1) into g_t2_prof (dev builds only)
@@ -528,8 +535,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc2_kernel(const A
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* bp = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t bars = base + T2_OFF_BARS;
-  // barrier map (8 B each): full[2] @0, empty[2] @24, S_ready[g][s] @48, P_ready[g][s] @80, O_done[g] @112, Q_ready[g] @128
-  const uint32_t bar_full = bars, bar_empty = bars + 24, bar_S = bars + 48, bar_P = bars + 80, bar_O = bars + 112, bar_Q = bars + 128;
+  // barrier map (8 B each): full[2] @0, empty[2] @16, S_ready[g][k] @32, P_ready[g][k] @80, O_done[g] @128, Q_ready[g] @144
+  const uint32_t bar_full = bars, bar_empty = bars + 16, bar_S = bars + 32, bar_P = bars + 80, bar_O = bars + 128, bar_Q = bars + 144;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bp + T2_OFF_BARS + 192);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -554,11 +561,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc2_kernel(const A
 
   if (tid == 0) {
     for (int i = 0; i < T2_STAGES; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 2 + 8); }
-    for (int i = 0; i < 4; ++i) { mbar_init(bar_S + 8 * i, 1); mbar_init(bar_P + 8 * i, 4); }
+    for (int i = 0; i < 6; ++i) { mbar_init(bar_S + 8 * i, 1); mbar_init(bar_P + 8 * i, 4); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_O + 8 * i, 1); mbar_init(bar_Q + 8 * i, 4); }
     mbar_fence_init();
   }
-  // constant B tiles: selector (element [key, 16 i + c] = 1 iff c / 4 == i and c % 4 < 3) and ones
+  // constant selector B tile: element [key, 16 i + c] = 1 iff c / 4 == i and c % 4 < 3
   for (int idx = tid; idx < 64 * 8; idx += TC_THREADS) {
     const int k = idx >> 3, ch = idx & 7;                         // 16-byte chunk ch = columns 8 ch .. 8 ch + 7
     uint32_t w[4];
@@ -571,8 +578,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc2_kernel(const A
     }
     *reinterpret_cast<uint4*>(bp + T2_OFF_SEL + sw128_off(k, ch)) = make_uint4(w[0], w[1], w[2], w[3]);
   }
-  for (int idx = tid; idx < 2048 / 16; idx += TC_THREADS)
-    *reinterpret_cast<uint4*>(bp + T2_OFF_ONES + 16 * idx) = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
   fence_async_smem();
   if (warp == 10) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
   fence_before();
@@ -625,23 +630,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc2_kernel(const A
     const unsigned long long qx2 = pk2(qx, qx), qy2 = pk2(qy, qy);
 
     float m[4];                                                   // reference maximum folded into S from the head's NEXT unit on
+    unsigned long long lsum[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) m[i] = -INFINITY;
+    for (int i = 0; i < 4; ++i) { m[i] = -INFINITY; lsum[i] = 0ull; }
 
     uint32_t ra[32], rb[32];
     const int total = 4 * nblk;
     if (nblk > 0) {
-      mbar_wait_parked(bar_S + 8 * (2 * g), 0);
+      mbar_wait_parked(bar_S + 8 * (3 * g), 0);
       fence_after();
-      tmem_ld32_nowait(trow + tc_slot(g, 0), ra);
-      tmem_ld32_nowait(trow + tc_slot(g, 0) + 32, rb);
+      tmem_ld32_nowait(trow + t2_slot(g, 0), ra);
+#if !T2_PIPE
+      tmem_ld32_nowait(trow + t2_slot(g, 0) + 32, rb);
+#endif
     }
     const unsigned long long neg1 = pk2(-1.0f, -1.0f);
     // exp2 + fp16 hi/lo split of one 32-key chunk held in r (in place); r already carries q.k - m, dc the (scaled) distances.
     // Software-pipelined by hand: the MUFU.EX2 of pair t + T2_DIST is issued before pair t is split, so that a result is consumed
     // ~T2_DIST x 16 XU cycles after its issue (ptxas otherwise schedules the dependent LOP3 a few slots behind its MUFU and the
     // in-order warp stalls on the scoreboard while the XU queue drains).
-    auto softmax_chunk = [&](uint32_t* r, const unsigned long long* dc) {
+    auto softmax_chunk = [&](uint32_t* r, const unsigned long long* dc, unsigned long long& ls) {
       constexpr int D = T2_DIST;
       float pv[32];
       auto ex = [&](int t) {                                      // pair t = elements (2t, 2t+1) of the chunk
@@ -649,7 +657,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc2_kernel(const A
 #if T2_ABL == 1
         pv[2 * t] = lo32(x); pv[2 * t + 1] = hi32(x);
 #else
-        pv[2 * t] = tc_ex2v(lo32(x)); pv[2 * t + 1] = tc_ex2v(hi32(x));
+        if (T2_POLY > 0 && (t % (T2_POLY > 0 ? T2_POLY : 1)) == (T2_POLY > 0 ? T2_POLY - 1 : 0)) {
+          const unsigned long long pp = tc_ex2_poly2(x);          // every T2_POLY-th pair on the FMA / integer pipes instead of the XU
+          pv[2 * t] = lo32(pp); pv[2 * t + 1] = hi32(pp);
+        } else {
+          pv[2 * t] = tc_ex2v(lo32(x)); pv[2 * t + 1] = tc_ex2v(hi32(x));
+        }
 #endif
       };
 #if T2_ABL == 2 || T2_ABL == 4
@@ -659,7 +672,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc2_kernel(const A
       auto sp = [&](int t) {
         const float p0 = pv[2 * t], p1 = pv[2 * t + 1];
         const float h0 = __uint_as_float(__float_as_uint(p0) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(p1) & 0xffffe000u);
-        const unsigned long long ll = fma2(pk2(h0, h1), neg1, pk2(p0, p1));
+        const unsigned long long pp = pk2(p0, p1);
+        ls = add2(ls, pp);
+        const unsigned long long ll = fma2(pk2(h0, h1), neg1, pp);
         hi[t] = tc_pack_h2(h0, h1);
         lo[t] = tc_pack_h2(lo32(ll), hi32(ll));
       };
@@ -729,19 +744,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc2_kernel(const A
 #pragma unroll
 #endif
       for (int i = 0; i < 4; ++i) {
-        const int u = 4 * j + i, s = u & 1;
-        const uint32_t slot = trow + tc_slot(g, s);
-        const uint32_t nslot = trow + tc_slot(g, s ^ 1);
+        const int u = 4 * j + i, k3 = u % 3, k3n = (u + 1) % 3;     // S/P slot of this unit and of the next
+        const uint32_t slot = trow + t2_slot(g, k3);
+        const uint32_t nslot = trow + t2_slot(g, k3n);
+        const uint32_t nbarS = bar_S + 8 * (3 * g + k3n), nparS = (uint32_t)(((u + 1) / 3) & 1);
         // head-indexed state through selects (constant register indices also when the loop is not unrolled)
         const float m_i = (i == 0) ? m[0] : (i == 1) ? m[1] : (i == 2) ? m[2] : m[3];
         const float bound_i = (i == 0) ? bound[0] : (i == 1) ? bound[1] : (i == 2) ? bound[2] : bound[3];
         tmem_wait_ld();
+#if T2_PIPE
+        // Chunk-level pipeline: every TMEM read is issued one chunk (half a unit) before its tcgen05.wait::ld and every store is
+        // waited for one chunk after its issue, so neither latency is exposed (both waits cover ALL outstanding accesses of the
+        // thread, hence the order: wait for the current half, THEN issue the read of the other half).
+        tmem_ld32_nowait(slot + 32, rb);                          // second half of this unit; rb was released by the previous store
+#endif
         T2_TICK(2);
         // ---- lazy reference: S already carries -m[i] (0 while m[i] = -inf). Only when the Cauchy-Schwarz bound admits an overflow
         // of the current reference is the block's row maximum looked at; a new reference shifts this unit's scores in registers,
         // rescales O_h / l_h and is published to the extension tile for the head's following units.
         const bool need = (m_i == -INFINITY) || (bound_i > m_i + TC_TAU);
         if (__any_sync(0xffffffffu, need)) {
+#if T2_PROF
+          if (prof_on) pc[7] += 1;                                // how often the row-maximum pass runs
+#endif
+#if T2_PIPE
+          tmem_wait_ld();                                         // rare path: the row maximum needs both halves
+#endif
           float rmax = -INFINITY;                                 // relative to the folded reference
 #pragma unroll
           for (int t = 0; t < 16; ++t) {
@@ -754,18 +782,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc2_kernel(const A
           else if (rmax > TC_TAU) { sc = tc_ex2(-rmax); m_new = m_i + rmax; delta = -rmax; }
           if (i == 0) m[0] = m_new; else if (i == 1) m[1] = m_new; else if (i == 2) m[2] = m_new; else m[3] = m_new;
           if (__any_sync(0xffffffffu, sc != 1.0f)) {
-            // every PV / row-sum MMA on head i issued so far has completed (in-order MMA pipe, S_ready of this unit waited)
+            // every PV MMA on head i issued so far has completed: PV of unit u - 4 was issued before QK^T of unit u - 1, whose
+            // S_ready this warp has waited for (in-order MMA pipe)
             uint32_t o[16];
-            tmem_ld16_nowait(trow + tc_ocol(4 * g + i), o);
+            tmem_ld16_nowait(trow + t2_ocol(4 * g + i), o);
             tmem_wait_ld();
 #pragma unroll
             for (int t = 0; t < 16; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) * sc);
-            tmem_st16_nowait(trow + tc_ocol(4 * g + i), o);
-            tmem_ld16_nowait(trow + t2_lcol(4 * g + i), o);
-            tmem_wait_ld();
-#pragma unroll
-            for (int t = 0; t < 16; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) * sc);
-            tmem_st16_nowait(trow + t2_lcol(4 * g + i), o);
+            tmem_st16_nowait(trow + t2_ocol(4 * g + i), o);
+            const unsigned long long sc2 = pk2(sc, sc);
+            if (i == 0) lsum[0] = mul2(lsum[0], sc2); else if (i == 1) lsum[1] = mul2(lsum[1], sc2);
+            else if (i == 2) lsum[2] = mul2(lsum[2], sc2); else lsum[3] = mul2(lsum[3], sc2);
           }
           if (__any_sync(0xffffffffu, delta != 0.f)) {
             const unsigned long long d2 = pk2(delta, delta);
@@ -790,53 +817,66 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc2_kernel(const A
             }
           }
         }
-        softmax_chunk(ra, db);
-#if T2_LATE_S
-        // A barrier test costs ~180 cycles even when the phase is complete (tools/tc_probe.cu): test S_ready of the next unit and
-        // the next block's full barrier here, one chunk before the results are needed (ahead of the TMEM store, which ptxas does
-        // not move it across), and only park on them if that test failed.
+        unsigned long long ls = (i == 0) ? lsum[0] : (i == 1) ? lsum[1] : (i == 2) ? lsum[2] : lsum[3];
+        // A barrier test costs ~180 cycles even when the phase is complete (tools/tc_probe.cu): S_ready of the next unit and the
+        // next block's full barrier are tested one chunk before the results are needed and only parked on if that test failed.
         bool s_ok = false;
-        if (u + 1 < total) s_ok = mbar_test_wait(bar_S + 8 * (2 * g + (s ^ 1)), (uint32_t)(((u + 1) >> 1) & 1));
+#if T2_PIPE
+        if (u + 1 < total) s_ok = mbar_test_wait(nbarS, nparS);
         if (i == 3 && j + 1 < nblk) f_ok = mbar_test_wait(bar_full + 8 * ((j + 1) % T2_STAGES), (uint32_t)(((j + 1) / T2_STAGES) & 1));
-#endif
+        softmax_chunk(ra, db, ls);
+        if (u > 0) {                                              // P of the PREVIOUS unit: its last store was issued one chunk ago
+          tmem_wait_st();
+          fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_P + 8 * (3 * g + (k3 + 2) % 3));
+        }
         tmem_st32_nowait(slot, ra);
         T2_TICK(3);
-#if !T2_LATE_S
-        if (u + 1 < total) {
-          mbar_wait_parked(bar_S + 8 * (2 * g + (s ^ 1)), (uint32_t)(((u + 1) >> 1) & 1));
+        tmem_wait_ld();                                           // second half of this unit (issued one chunk ago)
+        if (u + 1 < total) {                                      // first half of the next unit; ra was released by the store above
+          if (!s_ok) mbar_wait_parked(nbarS, nparS);
           fence_after();
           tmem_ld32_nowait(nslot, ra);
         }
-#endif
         T2_TICK(4);
-        softmax_chunk(rb, db + 16);
+        softmax_chunk(rb, db + 16, ls);
+        if (i == 0) lsum[0] = ls; else if (i == 1) lsum[1] = ls; else if (i == 2) lsum[2] = ls; else lsum[3] = ls;
         tmem_st32_nowait(slot + 32, rb);
         T2_TICK(5);
-#if T2_EARLY_LD
-        // second half of the next unit: issued BEFORE the store wait so that the TMEM read latency overlaps it (the store has
-        // captured rb's registers at issue; S of unit u + 1 was waited for above)
-        if (u + 1 < total) tmem_ld32_nowait(nslot + 32, rb);
-#endif
+#else
+        softmax_chunk(ra, db, ls);
+        if (u + 1 < total) s_ok = mbar_test_wait(nbarS, nparS);
+        if (i == 3 && j + 1 < nblk) f_ok = mbar_test_wait(bar_full + 8 * ((j + 1) % T2_STAGES), (uint32_t)(((j + 1) / T2_STAGES) & 1));
+        tmem_st32_nowait(slot, ra);
+        T2_TICK(3);
+        softmax_chunk(rb, db + 16, ls);
+        if (i == 0) lsum[0] = ls; else if (i == 1) lsum[1] = ls; else if (i == 2) lsum[2] = ls; else lsum[3] = ls;
+        tmem_st32_nowait(slot + 32, rb);
+        T2_TICK(5);
+        // S of the next unit is fetched at the unit end: with three slots its QK^T MMAs were issued two units ago
         tmem_wait_st();
         fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_P + 8 * (2 * g + s));
-#if T2_LATE_S
-        // S of the next unit is fetched only now: its QK^T MMAs sit behind this group's previous PV / row-sum MMAs and one
-        // barrier round trip (~1000 cycles after P_ready of unit u - 1), so waiting for it in the middle of the unit stalled the
-        // warp for ~350 cycles per unit (cycle accounting, tools/attn_prof.py); here it has long arrived.
+        if (lane == 0) mbar_arrive(bar_P + 8 * (3 * g + k3));
         if (u + 1 < total) {
-          if (!s_ok) mbar_wait_parked(bar_S + 8 * (2 * g + (s ^ 1)), (uint32_t)(((u + 1) >> 1) & 1));
+          if (!s_ok) mbar_wait_parked(nbarS, nparS);
           fence_after();
           tmem_ld32_nowait(nslot, ra);
           tmem_ld32_nowait(nslot + 32, rb);
         }
-#elif !T2_EARLY_LD
-        if (u + 1 < total) tmem_ld32_nowait(nslot + 32, rb);
-#endif
         T2_TICK(6);
+#endif
       }
     }
+#if T2_PIPE
+    if (nblk > 0) {                                               // P of the last unit
+      tmem_wait_st();
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_P + 8 * (3 * g + (total - 1) % 3));
+    }
+#endif
 #if T2_PROF
     if (prof_on && lane == 0) {
       for (int q = 0; q < 8; ++q) g_t2_prof[q] = pc[q];
@@ -849,7 +889,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc2_kernel(const A
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       uint32_t r[32];
-      if (nblk > 0) { tmem_ld32_nowait(trow + tc_ocol(4 * g) + 32 * c, r); tmem_wait_ld(); }
+      if (nblk > 0) { tmem_ld32_nowait(trow + t2_ocol(4 * g) + 32 * c, r); tmem_wait_ld(); }
       else {
 #pragma unroll
         for (int t = 0; t < 32; ++t) r[t] = 0u;
@@ -862,23 +902,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc2_kernel(const A
                                                                __uint_as_float(r[4 * t + 2]), __uint_as_float(r[4 * t + 3]));
       }
     }
-    {
-      float l[4] = {0.f, 0.f, 0.f, 0.f};
-      if (nblk > 0) {
+    if (rvalid) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint32_t r[16];
-          tmem_ld16_nowait(trow + t2_lcol(4 * g + i), r);
-          tmem_wait_ld();
-          l[i] = __uint_as_float(r[0]);
-        }
-      }
-      if (rvalid) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          p.Mpart[prow * 8 + 4 * g + i] = m[i];
-          p.Lpart[prow * 8 + 4 * g + i] = l[i];
-        }
+      for (int i = 0; i < 4; ++i) {
+        p.Mpart[prow * 8 + 4 * g + i] = m[i];
+        p.Lpart[prow * 8 + 4 * g + i] = lo32(lsum[i]) + hi32(lsum[i]);
       }
     }
   } else {
@@ -891,19 +919,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc2_kernel(const A
       const int total = 4 * nblk;
       const uint32_t qh_b = base + T2_OFF_Q + 16384 * g, ql_b = qh_b + 32768;
       const uint64_t ext_d = desc_sw128(base + T2_OFF_EXT + 32 * g);
-      const uint64_t ones_d = desc_sw128(base + T2_OFF_ONES);
       TC_ROLE_WAIT(bar_Q + 8 * g, 0);
       fence_after();
       auto issue_qk = [&](int u) {
         const int b = u >> 2, i = u & 3, st = b % T2_STAGES;
         if (i == 0) { TC_ROLE_WAIT(bar_full + 8 * st, (uint32_t)((b / T2_STAGES) & 1)); fence_after(); }
-        const uint32_t d = tm + tc_slot(g, u & 1);
+        const uint32_t d = tm + t2_slot(g, u % 3);
         const uint32_t kb = base + st * TC_IMG + 8192 * g + 32 * i;
         mma_ss(d, desc_sw128(qh_b + 32 * i), desc_sw128(kb), id64, 0);
         mma_ss(d, desc_sw128(ql_b + 32 * i), desc_sw128(kb), id64, 1);
         mma_ss(d, desc_sw128(qh_b + 32 * i), desc_sw128(kb + 16384), id64, 1);
         mma_ss(d, ext_d, desc_sw128(base + T2_OFF_SEL + 32 * i), id64, 1);          // - m_h (0 until the first reference is published)
-        mma_commit(bar_S + 8 * (2 * g + (u & 1)));
+        mma_commit(bar_S + 8 * (3 * g + u % 3));
       };
 #if T2_PROF
       const bool prof_on = (blockIdx.x == 5 && blockIdx.y == 1 && g == 0);
@@ -913,26 +940,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc2_kernel(const A
 #endif
       issue_qk(0);
       if (total > 1) issue_qk(1);
+      if (total > 2) issue_qk(2);
       T2_TICK(0);
       for (int u = 0; u < total; ++u) {
         const int b = u >> 2, i = u & 3, st = b % T2_STAGES, h = 4 * g + i;
-        TC_ROLE_WAIT(bar_P + 8 * (2 * g + (u & 1)), (uint32_t)((u >> 1) & 1));
+        TC_ROLE_WAIT(bar_P + 8 * (3 * g + u % 3), (uint32_t)((u / 3) & 1));
         fence_after();
         T2_TICK(1);
         const uint32_t vb = base + st * TC_IMG + TC_OFF_V + 2048 * h;
-        const uint32_t ps = tm + tc_slot(g, u & 1);
-        const uint32_t od = tm + tc_ocol(h), ld = tm + t2_lcol(h);
+        const uint32_t ps = tm + t2_slot(g, u % 3);
+        const uint32_t od = tm + t2_ocol(h);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           mma_ts(od, ps + 16 * ks, desc_sw128(vb + 32 * ks), id16, (b > 0 || ks > 0) ? 1u : 0u);
           mma_ts(od, ps + 16 * ks + 8, desc_sw128(vb + 32 * ks), id16, 1);
           mma_ts(od, ps + 16 * ks, desc_sw128(vb + 16384 + 32 * ks), id16, 1);
-          mma_ts(ld, ps + 16 * ks, ones_d, id16, (b > 0 || ks > 0) ? 1u : 0u);       // l_h += rowsum(P hi) + rowsum(P lo)
-          mma_ts(ld, ps + 16 * ks + 8, ones_d, id16, 1);
         }
         if (i == 3) mma_commit(bar_empty + 8 * st);
         T2_TICK(2);
-        if (u + 2 < total) issue_qk(u + 2);
+        if (u + 3 < total) issue_qk(u + 3);                          // into the slot whose P this unit's PV MMAs just consumed
         T2_TICK(3);
       }
       mma_commit(bar_O + 8 * g);

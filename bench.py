@@ -511,8 +511,17 @@ def main():
         nx = N if rows is None else rows[1] - rows[0]
         h2d = nx * feat * 4 + hg.edge_index.numel() * 8 + hg.pos.numel() * 4
 
+        server = None
+        if args.cuda_graph and world == 1 and host_batch is None:
+            from dgdm_histopath_lab_b200.loader import GraphServer
+            server = GraphServer(model, dev)       # public serving loop: staging + one captured graph per staging slot
+
         def run_e2e(k):
             g = None
+            if server is not None:
+                for out in server.run([hg] * k):
+                    g = out["graph_embedding"].cpu()
+                return g
             for d in DevicePrefetcher([hg] * k, dev, rows=rows):
                 g = model(d)["graph_embedding"].cpu()
             return g
@@ -528,13 +537,17 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": N * args.steps / dt, "unit": "nodes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": g.numel() * 4,
-               "ms_per_step": 1e3 * dt / args.steps, "staging": "pinned host -> device on a side stream, one step ahead"}
+               "ms_per_step": 1e3 * dt / args.steps, "staging": "pinned host -> device on a side stream, one step ahead",
+               "api": "loader.GraphServer (CUDA-graph replay per staging slot, validation read back with the result)" if server is not None
+               else "DGDMModel.forward on loader.DevicePrefetcher graphs (eager launches)"}
 
     # ---- per-kernel-class timing pass (CUDA events after every C-ABI call on the launching stream; eager launches)
     pk = peaks()
     if graphed is not None:
         step_resident = eager_step
         launches = args.steps * graphed.launches
+    step_resident()          # un-profiled eager pass first: the serving loop above captured its own graphs (private memory pools), so
+    torch.cuda.synchronize() # the caching allocator may have to cudaMalloc fresh blocks on the first eager forward after it
     ops.profile_begin()
     step_resident()
     prof = ops.profile_end()

@@ -27,7 +27,8 @@ class DevicePrefetcher:
         return t
 
     def _stage(self, g):
-        slot = self._slots[self._n & 1]
+        slot_index = self._n & 1
+        slot = self._slots[slot_index]
         self._n += 1
         # the slot was last used two graphs ago: everything enqueued on the consumer's stream so far includes that forward
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
@@ -43,6 +44,7 @@ class DevicePrefetcher:
                 d.batch = batch
             if self.rows is not None:
                 d.num_nodes = int(g.x.size(0))
+            d.__dict__["_stage_slot"] = slot_index           # which of the two staging buffer sets backs this graph (GraphServer)
             ev = torch.cuda.Event()
             ev.record(self.stream)
         return d, ev
@@ -61,3 +63,47 @@ class DevicePrefetcher:
             except StopIteration:
                 nxt = None
             yield d
+
+
+class GraphServer:
+    """Serving loop for a stream of host graphs (the reference's `evaluation/predictor.py:188-215` loop, one slide graph at a time):
+    DevicePrefetcher staging + ONE captured CUDA graph per staging slot. While graph i runs, graph i+1 is copied from pinned host
+    memory on a side stream into the other slot; a slot whose tensors keep their shapes replays its captured forward (CSR build and
+    input validation included) instead of issuing ~150 launches, and the validation result is read back together with the output —
+    one host synchronisation per graph, behind the forward instead of in front of it. Graphs of a new shape re-capture their slot;
+    node-partitioned models (no graph capture) and batched inputs run the eager forward.
+
+        server = GraphServer(model, device, return_embeddings=True)
+        for out in server.run(host_graphs):          # `out` tensors are static buffers: copy what must outlive the next step
+            emb = out["graph_embedding"].cpu()
+    """
+
+    def __init__(self, model, device, mode="inference", return_embeddings=False):
+        self.model, self.device, self.mode, self.return_embeddings = model, torch.device(device), mode, return_embeddings
+        self._runs = {}                      # slot index -> (key of the slot's tensors, captured callable)
+        self._pre = DevicePrefetcher([], self.device)        # ONE prefetcher for the server's lifetime: the captured graphs read its buffers
+        self.replays, self.captures = 0, 0
+
+    @staticmethod
+    def _key(d):
+        return tuple((k, tuple(getattr(d, k).shape), getattr(d, k).data_ptr()) for k in ("x", "edge_index", "edge_attr", "pos")
+                     if getattr(d, k, None) is not None)
+
+    def run(self, host_graphs, rows=None):
+        self._pre.graphs, self._pre.rows = host_graphs, rows
+        for d in self._pre:
+            slot = d.__dict__.get("_stage_slot", 0)
+            if getattr(self.model, "_comm", None) is not None or getattr(d, "batch", None) is not None:
+                yield self.model(d, self.mode, False, self.return_embeddings)
+                continue
+            key = self._key(d)
+            ent = self._runs.get(slot)
+            if ent is None or ent[0] != key:
+                # first graph of this shape in this slot: validated eager warm-up, then capture (the slot's tensors are static)
+                ent = (key, self.model.graphed(d, self.mode, self.return_embeddings, warmup=1, rebuild_structure=True, validate=True))
+                self._runs[slot] = ent
+                self.captures += 1
+            out = ent[1]()
+            ent[1].check()                   # reads the 32 validation bytes back: the replay has finished when this returns
+            self.replays += 1
+            yield out

@@ -289,6 +289,12 @@ class DGDMModel(nn.Module):
         if x.dtype != torch.float32 or ei.dtype != torch.int64 or not ei.is_cuda:
             raise ValidationError("x must be float32 and edge_index int64, both on the CUDA device")
         flags, stats = ops.validate_inputs(x.contiguous(), ei.contiguous(), self._num_nodes(data))   # one kernel, one readback
+        self._check_validation_result(flags, stats, x.numel())
+
+    @staticmethod
+    def _check_validation_result(flags, stats, n):
+        """Host side of `_validate_input_features` / the edge-index range checks (models/dgdm_model.py:646-710) on the 32 bytes the
+        validation kernel produced."""
         if flags[0]:
             raise ValidationError("Node features contain NaN values")
         if flags[1]:
@@ -298,7 +304,6 @@ class DGDMModel(nn.Module):
         if flags[3]:
             raise ValidationError("Edge index contains negative node indices")
         amax, s, ss = stats[0], stats[1], stats[2]
-        n = x.numel()
         if amax > 1000:
             warnings.warn(f"Large feature values detected: max={amax}")
         if n > 1:
@@ -337,7 +342,7 @@ class DGDMModel(nn.Module):
         except Exception as e:
             raise ModelInferenceError(f"Forward pass failed: {e}") from e
 
-    def graphed(self, data, mode="inference", return_embeddings=False, warmup=2, rebuild_structure=False):
+    def graphed(self, data, mode="inference", return_embeddings=False, warmup=2, rebuild_structure=False, validate=False):
         """CUDA-graph replay of `forward(data, mode, return_embeddings=...)` for small graphs, where the ~150 kernel launches and
         ~100 ctypes calls of a forward cost more than the kernels (host-bound below ~10k nodes). The forward is validated and
         warmed up eagerly (weight images, CSR, kernel attributes), captured once, and the returned callable replays it:
@@ -345,7 +350,9 @@ class DGDMModel(nn.Module):
         `data.x` / `data.pos` / `data.edge_attr` in place, so new features may be copied into those tensors between replays
         (same graph structure). Single-GPU inference / finetune forwards (capturing the node-partitioned forward — NCCL all-gathers and
         symmetric-memory barriers inside the graph — was tried and dead-locked on a 2-GPU box: not supported).
-        rebuild_structure=True keeps the CSR build inside the captured forward."""
+        rebuild_structure=True keeps the CSR build inside the captured forward. validate=True captures the input-validation kernel
+        as well: `run.check()` reads its 32 bytes back after a replay and raises exactly what `forward` raises for NaN / Inf features or
+        out-of-range edge indices (deferred validation: one host synchronisation per forward instead of one in front of it)."""
         if self._comm is not None or mode == "pretrain":
             raise ModelInferenceError("graphed() supports single-GPU inference / finetune forwards")
         for _ in range(max(1, warmup)):
@@ -357,15 +364,28 @@ class DGDMModel(nn.Module):
         with torch.no_grad(), torch.cuda.graph(graph, capture_error_mode="thread_local"):
             if rebuild_structure and hasattr(data, "__dict__") and getattr(data, "batch", None) is None:
                 data.__dict__.pop("_dgdm_ctx", None)          # (a batch vector needs a host read for the segment sizes: kept cached)
+            vbuf = None
+            if validate:
+                vbuf = ops.validate_inputs_device(data.x.contiguous(), data.edge_index.contiguous(), self._num_nodes(data))
             static_out = self.forward(data, mode, False, return_embeddings, validate=False)
         model = self
+        n_x = int(data.x.numel())
+
+        def check():
+            if vbuf is None:
+                return
+            host = vbuf.cpu()
+            try:
+                DGDMModel._check_validation_result(host[:4].tolist(), host[4:].view(torch.float32).tolist(), n_x)
+            except Exception as e:
+                raise ModelInferenceError(f"Input validation failed: {e}")
 
         def run():
             if model._weights_version() != versions:
                 raise ModelInferenceError("parameters changed since graphed() captured the forward: capture again")
             graph.replay()
             return static_out
-        run.graph, run.outputs, run.launches = graph, static_out, ops.LAUNCHES["kernels"] - l0
+        run.graph, run.outputs, run.launches, run.check = graph, static_out, ops.LAUNCHES["kernels"] - l0, check
         return run
 
     def _weights_version(self):

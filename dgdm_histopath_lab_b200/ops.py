@@ -503,12 +503,18 @@ def ddpm_update(x, eps_pred, noise, sqrt_1mac, inv_sqrt_ac, sqrt_alpha, sqrt_var
 
 
 # ------------------------------------------------------------------------------------------------ validation
-def validate_inputs(x, edge_index, N):
-    """One kernel + one 32-byte readback. Returns (flags[4] ints, stats[4] floats) on the host."""
+def validate_inputs_device(x, edge_index, N, buf=None):
+    """The validation kernel only: returns the 32-byte device buffer (flags[4] int32 | stats[4] float32), no readback — capturable."""
     lib = _lib.load()
-    buf = torch.empty(8, dtype=torch.int32, device=x.device)
+    if buf is None:
+        buf = torch.empty(8, dtype=torch.int32, device=x.device)
     flags, stats = buf[:4], buf[4:].view(torch.float32)
     _check(lib.dgdm_validate_inputs(_p(x), x.numel(), _p(edge_index), edge_index.numel(), N, _p(flags), _p(stats), _stream()),
            "dgdm_validate_inputs")
-    host = buf.cpu()
+    return buf
+
+
+def validate_inputs(x, edge_index, N):
+    """One kernel + one 32-byte readback. Returns (flags[4] ints, stats[4] floats) on the host."""
+    host = validate_inputs_device(x, edge_index, N).cpu()
     return host[:4].tolist(), host[4:].view(torch.float32).tolist()

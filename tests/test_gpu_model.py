@@ -283,6 +283,30 @@ def test_device_prefetcher_streams_graphs_in_order_and_reuses_buffers():
     assert part.x.shape == (70, 48) and part.num_nodes == 200 and torch.equal(part.x.cpu(), graphs[0].x[50:120])
 
 
+def test_graph_server_replays_equal_eager_forward_and_validate_late():
+    """loader.GraphServer: per-slot CUDA-graph replays (CSR build + validation captured) give bitwise the eager forward's outputs for
+    every graph of a stream, slots re-capture when the graph shape changes, a second run() reuses the captured graphs, and an invalid
+    input raises the forward's ModelInferenceError (validation read back after the replay)."""
+    from dgdm_histopath_lab_b200.loader import GraphServer
+    m = make_model(SMALL_CFG).to(DEV)
+    sizes = [200, 200, 200, 200, 260, 260, 260, 200]
+    graphs = [synth.tile_graph(n, 48, seed=70 + i).pin_memory() for i, n in enumerate(sizes)]
+    server = GraphServer(m, DEV, return_embeddings=True)
+    for rnd in range(2):
+        for i, out in enumerate(server.run(graphs)):
+            ref = m(graphs[i].to(DEV), return_embeddings=True)
+            for k in ("graph_embedding", "node_embeddings", "classification_logits"):
+                assert torch.equal(out[k], ref[k]), (rnd, i, k)
+    assert server.replays == 2 * len(sizes)
+    assert 4 <= server.captures <= 10          # two slots x shape changes, not one capture per graph
+    bad = synth.tile_graph(200, 48, seed=99)
+    bad.x[17, 3] = float("nan")
+    with pytest.raises(ModelInferenceError, match="NaN"):
+        list(server.run([graphs[0], bad.pin_memory(), graphs[1]]))
+    with pytest.raises(ModelInferenceError, match="NaN"):
+        m(bad.to(DEV))
+
+
 @pytest.mark.parametrize("kind", ["uniform", "jittered_grid", "clustered_with_duplicates", "collinear"])
 def test_knn2d_grid_equals_brute_force(kind):
     """uniform-grid ring search (O(N)) vs the brute-force fp64 distance rows: identical indices, order and distances, including

@@ -785,9 +785,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc2_kernel(const A
             const unsigned long long xb = sub2(pk2(__uint_as_float(rb[2 * t]), __uint_as_float(rb[2 * t + 1])), db[16 + t]);
             rmax = fmaxf(rmax, fmaxf(fmaxf(lo32(xa), hi32(xa)), fmaxf(lo32(xb), hi32(xb))));
           }
+          // The new reference is what the tensor core will subtract: -m as three fp16 pieces (hi + mid + lo reproduces an fp32 value
+          // to 2^-33; each piece is clamped to the finite fp16 range, because an infinite piece times the selector's zeros would put
+          // NaNs into the OTHER heads' scores). m_new is read back from the pieces, so the bookkeeping is exact by construction.
           float delta = 0.f, sc = 1.0f, m_new = m_i;
-          if (m_i == -INFINITY) { if (rmax > -INFINITY) { m_new = rmax; delta = -rmax; } }     // everything accumulated so far is 0
-          else if (rmax > TC_TAU) { sc = tc_ex2(-rmax); m_new = m_i + rmax; delta = -rmax; }
+          __half e0 = __float2half_rn(0.f), e1 = e0, e2 = e0;
+          const bool first = (m_i == -INFINITY);
+          if ((first && rmax > -INFINITY) || (!first && rmax > TC_TAU)) {
+            const float m_old = first ? 0.f : m_i;                 // reference folded into this unit's S
+            const float nm = -(m_old + rmax);
+            e0 = __float2half_rn(fminf(fmaxf(nm, -65000.f), 65000.f));
+            const float r1 = nm - __half2float(e0);
+            e1 = __float2half_rn(fminf(fmaxf(r1, -65000.f), 65000.f));
+            e2 = __float2half_rn(fminf(fmaxf(r1 - __half2float(e1), -65000.f), 65000.f));
+            m_new = -((__half2float(e0) + __half2float(e1)) + __half2float(e2));
+            delta = m_old - m_new;                                 // shift of this unit's scores (~ -rmax)
+            if (!first) sc = tc_ex2(delta);                        // everything accumulated so far is 0 when first
+          }
           if (i == 0) m[0] = m_new; else if (i == 1) m[1] = m_new; else if (i == 2) m[2] = m_new; else m[3] = m_new;
           if (__any_sync(0xffffffffu, sc != 1.0f)) {
             // every PV MMA on head i issued so far has completed: PV of unit u - 4 was issued before QK^T of unit u - 1, whose
@@ -812,12 +826,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc2_kernel(const A
               rb[2 * t] = (uint32_t)xb; rb[2 * t + 1] = (uint32_t)(xb >> 32);
             }
             if (delta != 0.f) {
-              // -m as three fp16 pieces (hi + mid + lo reproduces the fp32 value to 2^-33) in columns 4 i .. 4 i + 2 of the slice
-              const float nm = -m_new;
-              const __half e0 = __float2half_rn(nm);
-              const float r1 = nm - __half2float(e0);
-              const __half e1 = __float2half_rn(r1);
-              const __half e2 = __float2half_rn(r1 - __half2float(e1));
+              // publish the pieces in columns 4 i .. 4 i + 2 of this row's slice of the extension tile
               const uint32_t w0 = (uint32_t)__half_as_ushort(e0) | ((uint32_t)__half_as_ushort(e1) << 16);
               const uint32_t w1 = (uint32_t)__half_as_ushort(e2);
               *reinterpret_cast<uint2*>(ext_row + sw128_off(rl, 2 * g + (i >> 1)) + 8 * (i & 1)) = make_uint2(w0, w1);

@@ -218,6 +218,26 @@ def test_spatial_attention_large_scores_trigger_rescale():
     assert rel_err(out, ref)[0] < 5e-5
 
 
+def test_spatial_attention_reference_beyond_fp16_range():
+    """Head 0 gets scores of +-8e4 (log2 units): the reference maximum that the tcgen05 kernel folds into the QK^T MMA as fp16 pieces
+    exceeds the fp16 range, so the pieces have to be clamped and chained — no NaN / Inf anywhere (an infinite piece would poison the
+    other heads through the selector's zeros), head 0 averages over the keys that tie at the maximum, the other heads are unaffected."""
+    g = _gen(12)
+    n, D, H = 600, 128, 8
+    qkv = torch.randn(n, 3 * D, generator=g)
+    sgn = (torch.randint(0, 2, (n, 1), generator=g) * 2 - 1).float()
+    qkv[:, 0:16] = 120.0 * sgn                                   # q, head 0
+    qkv[:, D:D + 16] = 120.0 * sgn                               # k, head 0: q.k = +-230400 -> +-83k after the log2e / 4 scale
+    pos = torch.rand(n, 2, generator=g)
+    q, k, v = (qkv[:, i * D:(i + 1) * D].double().view(n, H, 16).transpose(0, 1) for i in range(3))
+    ref = (torch.softmax(q @ k.transpose(1, 2) / 4.0 - torch.cdist(pos.double(), pos.double()), -1) @ v).transpose(0, 1).reshape(n, D)
+    seg = torch.tensor([0, n], dtype=torch.int32, device=DEV)
+    out = ops.spatial_attention(qkv.to(DEV), pos.to(DEV), seg, 1, H, 1.0, precise=1)
+    assert torch.isfinite(out).all()
+    assert rel_err(out[:, 16:], ref[:, 16:])[0] < 2e-5           # heads 1..7
+    assert rel_err(out[:, :16], ref[:, :16])[0] < 1e-3           # head 0: fp32 scores of 8e4 carry ~1e-2 absolute rounding
+
+
 def test_attention_pool_vs_oracle():
     m = make_model(SMALL_CFG); sd = sd_cpu(m)
     x = torch.randn(300, 32, generator=_gen(2)); batch = torch.cat([torch.zeros(120), torch.ones(180)]).long()

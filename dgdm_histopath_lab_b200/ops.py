@@ -26,7 +26,7 @@ KERNELS_PER_CALL = {
     "dgdm_row_sqnorm_f64": 1, "dgdm_knn_cosine_tc": 6,
 }
 LAUNCHES = {"kernels": 0, "calls": 0}
-# MUFU (XU pipe) operations per attention score in spatial_attn_tc_kernel: one exp2 per (row, key, head) + the distance sqrt of a
+# MUFU (XU pipe) operations per attention score in spatial_attn_tc2_kernel (and its predecessor): one exp2 per (row, key, head) + the distance sqrt of a
 # (row, key) shared by the heads of a softmax group (bench.py's roofline denominator; see attention_tc.cu)
 ATTN_MUFU_PER_SCORE = 1.25
 _PROFILE = None      # when set to a list: (name, start_event, end_event) per C call (bench.py's per-kernel timing pass)

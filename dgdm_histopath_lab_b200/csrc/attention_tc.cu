@@ -649,9 +649,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc2_kernel(const A
     }
     const unsigned long long neg1 = pk2(-1.0f, -1.0f);
     // exp2 + fp16 hi/lo split of one 32-key chunk held in r (in place); r already carries q.k - m, dc the (scaled) distances.
-    // Software-pipelined by hand: the MUFU.EX2 of pair t + T2_DIST is issued before pair t is split, so that a result is consumed
-    // ~T2_DIST x 16 XU cycles after its issue (ptxas otherwise schedules the dependent LOP3 a few slots behind its MUFU and the
-    // in-order warp stalls on the scoreboard while the XU queue drains).
+    // Written as a software pipeline (the MUFU.EX2 of pair t + T2_DIST before the split of pair t). ptxas re-schedules the chunk
+    // anyway: it paces the MUFUs with 8-cycle issue stalls and places each dependent LOP3 two to three MUFUs behind its producer
+    // (six scoreboards), so the source order only fixes which registers are live; kept because it is the order that was measured.
     auto softmax_chunk = [&](uint32_t* r, const unsigned long long* dc, unsigned long long& ls) {
       constexpr int D = T2_DIST;
       float pv[32];

@@ -539,9 +539,10 @@ def main():
             t = torch.tensor([dt], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        e2e = {"value": N * args.steps / dt, "unit": "nodes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": g.numel() * 4,
+        e2e = {"value": N * args.steps / dt, "unit": "nodes/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": g.numel() * 4 + (32 if server is not None else 0),      # result (+ the 32 validation bytes)
                "ms_per_step": 1e3 * dt / args.steps, "staging": "pinned host -> device on a side stream, one step ahead",
-               "api": "loader.GraphServer (CUDA-graph replay per staging slot, validation read back with the result)" if server is not None
+               "api": "loader.GraphServer (CUDA-graph replay per staging slot; result + validation bytes read back on their own stream behind the next replay)" if server is not None
                else "DGDMModel.forward on loader.DevicePrefetcher graphs (eager launches)"}
 
     # ---- per-kernel-class timing pass (CUDA events after every C-ABI call on the launching stream; eager launches)

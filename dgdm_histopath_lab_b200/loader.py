@@ -67,21 +67,28 @@ class DevicePrefetcher:
 
 class GraphServer:
     """Serving loop for a stream of host graphs (the reference's `evaluation/predictor.py:188-215` loop, one slide graph at a time):
-    DevicePrefetcher staging + ONE captured CUDA graph per staging slot. While graph i runs, graph i+1 is copied from pinned host
-    memory on a side stream into the other slot; a slot whose tensors keep their shapes replays its captured forward (CSR build and
-    input validation included) instead of issuing ~150 launches, and the validation result is read back together with the output —
-    one host synchronisation per graph, behind the forward instead of in front of it. Graphs of a new shape re-capture their slot;
-    node-partitioned models (no graph capture) and batched inputs run the eager forward.
+    DevicePrefetcher staging + ONE captured CUDA graph per staging slot + a read-back stream. While graph i runs, graph i+1 is
+    copied from pinned host memory on a side stream into the other slot; a slot whose tensors keep their shapes replays its
+    captured forward (CSR build and input validation included) instead of issuing ~150 launches. The replay of graph i+1 is
+    enqueued BEFORE the results of graph i are read back (the two slots own separate output buffers), and the read-back — the
+    fetched outputs plus the 32 validation bytes — runs on its own stream behind an event, so the device never waits for the
+    host. Validation keeps the forward's error behaviour (NaN / Inf features, out-of-range edge indices raise
+    `ModelInferenceError` at the position of the offending graph). Graphs of a new shape re-capture their slot; node-partitioned
+    models (no graph capture) and batched inputs run the eager forward.
 
         server = GraphServer(model, device, return_embeddings=True)
-        for out in server.run(host_graphs):          # `out` tensors are static buffers: copy what must outlive the next step
-            emb = out["graph_embedding"].cpu()
+        for out in server.run(host_graphs):          # fetched keys are host tensors; the rest are the slot's static device buffers,
+            emb = out["graph_embedding"]             # valid until the next-but-one graph: copy what must live longer
     """
 
-    def __init__(self, model, device, mode="inference", return_embeddings=False):
+    def __init__(self, model, device, mode="inference", return_embeddings=False, fetch=("graph_embedding",)):
         self.model, self.device, self.mode, self.return_embeddings = model, torch.device(device), mode, return_embeddings
+        self.fetch = tuple(fetch)
         self._runs = {}                      # slot index -> (key of the slot's tensors, captured callable)
         self._pre = DevicePrefetcher([], self.device)        # ONE prefetcher for the server's lifetime: the captured graphs read its buffers
+        self._rb_stream = torch.cuda.Stream(device=self.device)
+        self._host = [{}, {}]                # pinned read-back buffers, two sets (results of consecutive graphs)
+        self._n_out = 0
         self.replays, self.captures = 0, 0
 
     @staticmethod
@@ -89,11 +96,47 @@ class GraphServer:
         return tuple((k, tuple(getattr(d, k).shape), getattr(d, k).data_ptr()) for k in ("x", "edge_index", "edge_attr", "pos")
                      if getattr(d, k, None) is not None)
 
+    def _pinned(self, hs, key, t):
+        b = hs.get(key)
+        if b is None or b.shape != t.shape or b.dtype != t.dtype:
+            b = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            hs[key] = b
+        return b
+
+    def _finish(self, pending):
+        """Read the fetched outputs and the validation bytes of a replay back on the read-back stream, check, build the result."""
+        out, run, ev = pending
+        hs = self._host[self._n_out & 1]
+        self._n_out += 1
+        res = dict(out)
+        with torch.cuda.stream(self._rb_stream):
+            self._rb_stream.wait_event(ev)
+            for k in self.fetch:
+                v = out.get(k)
+                if torch.is_tensor(v):
+                    res[k] = self._pinned(hs, k, v).copy_(v, non_blocking=True)
+            vb = run.validation_buffer
+            flags = None if vb is None else self._pinned(hs, "_validation", vb).copy_(vb, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self._rb_stream)
+        done.synchronize()
+        if flags is not None:
+            from .errors import ModelInferenceError
+            try:
+                self.model._check_validation_result(flags[:4].tolist(), flags[4:].view(torch.float32).tolist(), run.n_x)
+            except Exception as e:
+                raise ModelInferenceError(f"Input validation failed: {e}")
+        return res
+
     def run(self, host_graphs, rows=None):
         self._pre.graphs, self._pre.rows = host_graphs, rows
+        pending = None
         for d in self._pre:
             slot = d.__dict__.get("_stage_slot", 0)
             if getattr(self.model, "_comm", None) is not None or getattr(d, "batch", None) is not None:
+                if pending is not None:
+                    res, pending = self._finish(pending), None
+                    yield res
                 yield self.model(d, self.mode, False, self.return_embeddings)
                 continue
             key = self._key(d)
@@ -103,7 +146,12 @@ class GraphServer:
                 ent = (key, self.model.graphed(d, self.mode, self.return_embeddings, warmup=1, rebuild_structure=True, validate=True))
                 self._runs[slot] = ent
                 self.captures += 1
-            out = ent[1]()
-            ent[1].check()                   # reads the 32 validation bytes back: the replay has finished when this returns
+            out = ent[1]()                   # enqueue the replay of THIS graph ...
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
             self.replays += 1
-            yield out
+            if pending is not None:          # ... and only then read the previous graph's results back
+                yield self._finish(pending)
+            pending = (out, ent[1], ev)
+        if pending is not None:
+            yield self._finish(pending)

@@ -386,6 +386,7 @@ class DGDMModel(nn.Module):
             graph.replay()
             return static_out
         run.graph, run.outputs, run.launches, run.check = graph, static_out, ops.LAUNCHES["kernels"] - l0, check
+        run.validation_buffer, run.n_x = vbuf, n_x        # for callers that read the 32 bytes back on their own stream (GraphServer)
         return run
 
     def _weights_version(self):

@@ -285,24 +285,32 @@ def test_device_prefetcher_streams_graphs_in_order_and_reuses_buffers():
 
 def test_graph_server_replays_equal_eager_forward_and_validate_late():
     """loader.GraphServer: per-slot CUDA-graph replays (CSR build + validation captured) give bitwise the eager forward's outputs for
-    every graph of a stream, slots re-capture when the graph shape changes, a second run() reuses the captured graphs, and an invalid
-    input raises the forward's ModelInferenceError (validation read back after the replay)."""
+    every graph of a stream (fetched keys arrive as host tensors, read back behind the NEXT graph's replay), slots re-capture when
+    the graph shape changes, a second run() reuses the captured graphs, and an invalid input raises the forward's
+    ModelInferenceError at its position in the stream (validation read back after the replay)."""
     from dgdm_histopath_lab_b200.loader import GraphServer
     m = make_model(SMALL_CFG).to(DEV)
     sizes = [200, 200, 200, 200, 260, 260, 260, 200]
     graphs = [synth.tile_graph(n, 48, seed=70 + i).pin_memory() for i, n in enumerate(sizes)]
-    server = GraphServer(m, DEV, return_embeddings=True)
+    server = GraphServer(m, DEV, return_embeddings=True, fetch=("graph_embedding", "classification_logits"))
     for rnd in range(2):
+        n_seen = 0
         for i, out in enumerate(server.run(graphs)):
             ref = m(graphs[i].to(DEV), return_embeddings=True)
+            assert not out["graph_embedding"].is_cuda and out["node_embeddings"].is_cuda
             for k in ("graph_embedding", "node_embeddings", "classification_logits"):
-                assert torch.equal(out[k], ref[k]), (rnd, i, k)
+                assert torch.equal(out[k].cpu(), ref[k].cpu()), (rnd, i, k)
+            n_seen += 1
+        assert n_seen == len(sizes)
     assert server.replays == 2 * len(sizes)
     assert 4 <= server.captures <= 10          # two slots x shape changes, not one capture per graph
     bad = synth.tile_graph(200, 48, seed=99)
     bad.x[17, 3] = float("nan")
+    got = []
     with pytest.raises(ModelInferenceError, match="NaN"):
-        list(server.run([graphs[0], bad.pin_memory(), graphs[1]]))
+        for out in server.run([graphs[0], bad.pin_memory(), graphs[1]]):
+            got.append(out["graph_embedding"].clone())
+    assert len(got) == 1                         # the graph in front of the bad one is delivered, the bad one raises
     with pytest.raises(ModelInferenceError, match="NaN"):
         m(bad.to(DEV))
 

@@ -511,22 +511,15 @@ def main():
         nx = N if rows is None else rows[1] - rows[0]
         h2d = nx * feat * 4 + hg.edge_index.numel() * 8 + hg.pos.numel() * 4
 
-        server = None
-        if args.cuda_graph and world == 1 and host_batch is None:
-            from dgdm_histopath_lab_b200.loader import GraphServer
-            server = GraphServer(model, dev)       # public serving loop: staging + one captured graph per staging slot
-
-        pre = DevicePrefetcher([], dev, rows=rows)
+        # public serving loop: staging one graph ahead, a captured CUDA graph per staging slot at one GPU (eager launches when the model
+        # is node-partitioned or --cuda-graph 0), validation and result read back on their own stream behind the next forward
+        from dgdm_histopath_lab_b200.loader import GraphServer
+        server = GraphServer(model, dev, use_graphs=bool(args.cuda_graph))
 
         def run_e2e(k):
             g = None
-            if server is not None:
-                for out in server.run([hg] * k):
-                    g = out["graph_embedding"].cpu()
-                return g
-            pre.graphs = [hg] * k              # ONE prefetcher: its staging buffers are allocated in the warm-up call, not in the timed region
-            for d in pre:
-                g = model(d)["graph_embedding"].cpu()
+            for out in server.run([hg] * k, rows=rows):
+                g = out["graph_embedding"].cpu()
             return g
 
         run_e2e(2)
@@ -540,10 +533,10 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": N * args.steps / dt, "unit": "nodes/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": g.numel() * 4 + (32 if server is not None else 0),      # result (+ the 32 validation bytes)
+               "d2h_bytes_per_step": g.numel() * 4 + 32,                                     # result + the 32 validation bytes
                "ms_per_step": 1e3 * dt / args.steps, "staging": "pinned host -> device on a side stream, one step ahead",
-               "api": "loader.GraphServer (CUDA-graph replay per staging slot; result + validation bytes read back on their own stream behind the next replay)" if server is not None
-               else "DGDMModel.forward on loader.DevicePrefetcher graphs (eager launches)"}
+               "api": "loader.GraphServer: " + ("CUDA-graph replay per staging slot" if server.replays else "eager launches (node-partitioned / --cuda-graph 0)")
+                      + "; result + validation bytes read back on their own stream behind the next forward"}
 
     # ---- per-kernel-class timing pass (CUDA events after every C-ABI call on the launching stream; eager launches)
     pk = peaks()

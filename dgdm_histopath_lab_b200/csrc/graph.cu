@@ -42,13 +42,24 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int* __restr
 }
 
 // ------------------------------------------------------------------------------------------ CSR build
-__global__ void count_dst_kernel(const long long* __restrict__ ei, int E, int* __restrict__ cnt) {
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) atomicAdd(cnt + (int)ei[(size_t)E + e], 1);
+// Edges whose source or destination lies outside [0, N) are left out of the CSR (both passes apply the same test), so a forward
+// whose input validation is read back BEHIND it (captured graphs, loader.GraphServer) cannot index out of bounds; the validation
+// kernel flags such inputs and the host raises the reference's error for them.
+__device__ __forceinline__ bool edge_in_range(long long s, long long d, int N) {
+  return (unsigned long long)s < (unsigned long long)N && (unsigned long long)d < (unsigned long long)N;
 }
-__global__ void fill_unordered_kernel(const long long* __restrict__ ei, int E, const int* __restrict__ rowptr,
+__global__ void count_dst_kernel(const long long* __restrict__ ei, int E, int N, int* __restrict__ cnt) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+    const long long s = ei[e], d = ei[(size_t)E + e];
+    if (edge_in_range(s, d, N)) atomicAdd(cnt + (int)d, 1);
+  }
+}
+__global__ void fill_unordered_kernel(const long long* __restrict__ ei, int E, int N, const int* __restrict__ rowptr,
                                       int* __restrict__ cursor, int* __restrict__ tmp_eid) {
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
-    const int d = (int)ei[(size_t)E + e];
+    const long long s = ei[e], dl = ei[(size_t)E + e];
+    if (!edge_in_range(s, dl, N)) continue;
+    const int d = (int)dl;
     tmp_eid[rowptr[d] + atomicAdd(cursor + d, 1)] = e;
   }
 }
@@ -430,11 +441,11 @@ extern "C" int dgdm_csr_build(const int64_t* edge_index, int E, int N, int* rowp
   int* cnt = work; int* cursor = work + (N + 1); int* tmp_eid = work + 2 * (N + 1);
   if (cudaMemsetAsync(cnt, 0, sizeof(int) * 2 * (N + 1), s) != cudaSuccess) return DGDM_ERR_LAUNCH;
   const long long* ei = (const long long*)edge_index;
-  if (E > 0) count_dst_kernel<<<grid1d(E), 256, 0, s>>>(ei, E, cnt);
+  if (E > 0) count_dst_kernel<<<grid1d(E), 256, 0, s>>>(ei, E, N, cnt);
   launch_exclusive_scan(cnt, rowptr, N, tmp_eid, E + 16, s);      // tmp_eid is free until fill_unordered_kernel
   dinv_kernel<<<grid1d(N), 256, 0, s>>>(rowptr, N, dinv);
   if (E > 0) {
-    fill_unordered_kernel<<<grid1d(E), 256, 0, s>>>(ei, E, rowptr, cursor, tmp_eid);
+    fill_unordered_kernel<<<grid1d(E), 256, 0, s>>>(ei, E, N, rowptr, cursor, tmp_eid);
     order_rows_kernel<<<(N + 7) / 8, 256, 0, s>>>(ei, E, rowptr, tmp_eid, dinv, N, col, eid, norm);
   }
   DGDM_CHECK_LAUNCH();

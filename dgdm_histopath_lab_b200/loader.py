@@ -65,6 +65,13 @@ class DevicePrefetcher:
             yield d
 
 
+class _Deferred:
+    """What `_finish` needs of a forward whose validation read-back is still pending."""
+
+    def __init__(self, validation_buffer, n_x):
+        self.validation_buffer, self.n_x = validation_buffer, n_x
+
+
 class GraphServer:
     """Serving loop for a stream of host graphs (the reference's `evaluation/predictor.py:188-215` loop, one slide graph at a time):
     DevicePrefetcher staging + ONE captured CUDA graph per staging slot + a read-back stream. While graph i runs, graph i+1 is
@@ -74,22 +81,23 @@ class GraphServer:
     fetched outputs plus the 32 validation bytes — runs on its own stream behind an event, so the device never waits for the
     host. Validation keeps the forward's error behaviour (NaN / Inf features, out-of-range edge indices raise
     `ModelInferenceError` at the position of the offending graph). Graphs of a new shape re-capture their slot; node-partitioned
-    models (no graph capture) and batched inputs run the eager forward.
+    models (no graph capture) and batched inputs run eager launches through the same pipeline (validation kernel enqueued without
+    its read-back, results read back behind the next graph's forward).
 
         server = GraphServer(model, device, return_embeddings=True)
         for out in server.run(host_graphs):          # fetched keys are host tensors; the rest are the slot's static device buffers,
             emb = out["graph_embedding"]             # valid until the next-but-one graph: copy what must live longer
     """
 
-    def __init__(self, model, device, mode="inference", return_embeddings=False, fetch=("graph_embedding",)):
+    def __init__(self, model, device, mode="inference", return_embeddings=False, fetch=("graph_embedding",), use_graphs=True):
         self.model, self.device, self.mode, self.return_embeddings = model, torch.device(device), mode, return_embeddings
-        self.fetch = tuple(fetch)
+        self.fetch, self.use_graphs = tuple(fetch), use_graphs
         self._runs = {}                      # slot index -> (key of the slot's tensors, captured callable)
         self._pre = DevicePrefetcher([], self.device)        # ONE prefetcher for the server's lifetime: the captured graphs read its buffers
         self._rb_stream = torch.cuda.Stream(device=self.device)
         self._host = [{}, {}]                # pinned read-back buffers, two sets (results of consecutive graphs)
         self._n_out = 0
-        self.replays, self.captures = 0, 0
+        self.replays, self.captures, self.eager = 0, 0, 0
 
     @staticmethod
     def _key(d):
@@ -133,11 +141,22 @@ class GraphServer:
         pending = None
         for d in self._pre:
             slot = d.__dict__.get("_stage_slot", 0)
-            if getattr(self.model, "_comm", None) is not None or getattr(d, "batch", None) is not None:
+            if not self.use_graphs or getattr(self.model, "_comm", None) is not None or getattr(d, "batch", None) is not None:
+                # eager launches (node-partitioned model: NCCL and symmetric-memory barriers are not capturable; batches: a host
+                # read for the segment sizes), same pipeline: the validation kernel is enqueued without its read-back, so the host
+                # enqueues the whole forward without synchronising, and the results are read back behind the next graph's forward
+                from .errors import ModelInferenceError
+                try:
+                    vbuf = self.model._validate_forward_inputs(d, self.mode, False, self.return_embeddings, deferred=True)
+                except Exception as e:
+                    raise ModelInferenceError(f"Input validation failed: {e}")
+                out = self.model(d, self.mode, False, self.return_embeddings, validate=False)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.device))
+                self.eager += 1
                 if pending is not None:
-                    res, pending = self._finish(pending), None
-                    yield res
-                yield self.model(d, self.mode, False, self.return_embeddings)
+                    yield self._finish(pending)
+                pending = (out, _Deferred(vbuf, int(d.x.numel())), ev)
                 continue
             key = self._key(d)
             ent = self._runs.get(slot)

@@ -267,7 +267,9 @@ class DGDMModel(nn.Module):
             nn.init.constant_(module.bias, 0)
 
     # -------------------------------------------------------------------------------------- validation
-    def _validate_forward_inputs(self, data, mode, return_attention, return_embeddings):
+    def _validate_forward_inputs(self, data, mode, return_attention, return_embeddings, deferred=False):
+        """deferred=True: the host-side structure checks run now, the validation kernel is enqueued without its read-back and its
+        32-byte device buffer is returned — the caller reads it back behind the forward (`_check_validation_result`)."""
         if not isinstance(data, GRAPH_TYPES):
             raise ValidationError(f"Expected Data or Batch, got {type(data)}")
         for attr in ("x", "edge_index"):
@@ -288,8 +290,11 @@ class DGDMModel(nn.Module):
         _require_cuda(x)
         if x.dtype != torch.float32 or ei.dtype != torch.int64 or not ei.is_cuda:
             raise ValidationError("x must be float32 and edge_index int64, both on the CUDA device")
+        if deferred:
+            return ops.validate_inputs_device(x.contiguous(), ei.contiguous(), self._num_nodes(data))
         flags, stats = ops.validate_inputs(x.contiguous(), ei.contiguous(), self._num_nodes(data))   # one kernel, one readback
         self._check_validation_result(flags, stats, x.numel())
+        return None
 
     @staticmethod
     def _check_validation_result(flags, stats, n):

@@ -311,6 +311,21 @@ def test_graph_server_replays_equal_eager_forward_and_validate_late():
         for out in server.run([graphs[0], bad.pin_memory(), graphs[1]]):
             got.append(out["graph_embedding"].clone())
     assert len(got) == 1                         # the graph in front of the bad one is delivered, the bad one raises
+    # out-of-range / negative edge indices reach the captured CSR build before their validation is read back: the build leaves such
+    # edges out instead of indexing out of bounds, the error is the forward's, and the device stays usable
+    for val, msg in ((10 ** 6, "invalid node indices"), (-3, "negative node indices")):
+        bad_e = synth.tile_graph(200, 48, seed=98)
+        bad_e.edge_index[0, 5] = val
+        with pytest.raises(ModelInferenceError, match=msg):
+            list(server.run([graphs[0], bad_e.pin_memory(), graphs[1]]))
+        with pytest.raises(ModelInferenceError, match=msg):
+            m(bad_e.to(DEV))
+    eager = GraphServer(m, DEV, return_embeddings=True, use_graphs=False)      # eager launches through the same deferred pipeline
+    for i, out in enumerate(eager.run(graphs[:4])):
+        assert torch.equal(out["node_embeddings"], m(graphs[i].to(DEV), return_embeddings=True)["node_embeddings"])
+    assert eager.eager == 4 and eager.captures == 0
+    with pytest.raises(ModelInferenceError, match="NaN"):
+        list(eager.run([graphs[0], bad.pin_memory()]))
     with pytest.raises(ModelInferenceError, match="NaN"):
         m(bad.to(DEV))
 

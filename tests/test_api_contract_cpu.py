@@ -90,3 +90,21 @@ def test_non_default_normalizations_construct_like_the_reference(norm, cls):
         warnings.simplefilter("ignore")
         m = DGDMModel(node_features=48, hidden_dims=[64, 32, 32], attention_heads=2, num_classes=3, normalization=norm)
     assert isinstance(m.feature_encoder.encoder[1], cls) and isinstance(m.graph_encoder.norm_layers[0], cls)
+
+
+def test_validation_result_interpretation_matches_the_reference_messages():
+    """Host half of the one-kernel input validation (models/dgdm_model.py:646-710): the 4 flags map to the reference's error texts in
+    its order of checks, the statistics to its warnings. The same function serves the immediate read-back of `forward` and the
+    deferred one of `graphed(validate=True)` / `loader.GraphServer`."""
+    from dgdm_histopath_lab_b200.errors import ValidationError
+    chk = DGDMModel._check_validation_result
+    ok_stats = [1.0, 10.0, 200.0, 0.0]                       # max |x|, sum, sum of squares
+    chk([0, 0, 0, 0], ok_stats, 100)
+    for flags, msg in (([1, 1, 1, 1], "NaN"), ([0, 1, 1, 1], "infinity"), ([0, 0, 1, 1], "invalid node indices"),
+                       ([0, 0, 0, 1], "negative node indices")):
+        with pytest.raises(ValidationError, match=msg):
+            chk(flags, ok_stats, 100)
+    with pytest.warns(UserWarning, match="Large feature values"):
+        chk([0, 0, 0, 0], [5000.0, 10.0, 200.0, 0.0], 100)
+    with pytest.warns(UserWarning, match="very low variance"):
+        chk([0, 0, 0, 0], [1.0, 100.0, 100.0, 0.0], 100)     # all ones: variance 0

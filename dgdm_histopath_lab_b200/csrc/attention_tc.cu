@@ -102,6 +102,12 @@ __device__ __forceinline__ float tc_ex2v(float x) { float y; asm volatile("ex2.a
 #ifndef T2_ROLL
 #define T2_ROLL 0          // 1 / 2: head loop rolled / unrolled twice (less code) — measured 37.9 / 36.1 ms vs 33.1 ms fully unrolled
 #endif
+#ifndef T2_WATCH
+// 1: the fourth role warp polls the S_ready barriers and publishes a unit counter (st.release / ld.acquire on shared memory), so that
+// the softmax warps replace their one barrier test per unit (~180 cycles, 7 % of all samples) by a load. Correct (attention tests
+// green) but MEASURED NOT FASTER: 33.52 vs 33.18 ms — the stall overlaps the scheduler's other warp; off by default.
+#define T2_WATCH 0
+#endif
 #ifndef T2_JUNROLL
 #define T2_JUNROLL 1       // 2: key-block loop unrolled twice — measured 34.08 vs 33.16 ms (instruction-cache misses, ncu no_instruction 0.5)
 #endif
@@ -541,6 +547,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc2_kernel(const A
   // barrier map (8 B each): full[2] @0, empty[2] @16, S_ready[g][k] @32, P_ready[g][k] @80, O_done[g] @128, Q_ready[g] @144
   const uint32_t bar_full = bars, bar_empty = bars + 16, bar_S = bars + 32, bar_P = bars + 80, bar_O = bars + 128, bar_Q = bars + 144;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bp + T2_OFF_BARS + 192);
+  // watcher words (T2_WATCH): [0], [1] = number of units of group 0 / 1 whose S_ready the watcher warp has observed, [2] = softmax
+  // warps that have left their loop
+  const uint32_t wflag = bars + 168;
+  (void)wflag;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int seg = -1, row0 = 0;
@@ -567,6 +577,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc2_kernel(const A
     for (int i = 0; i < 6; ++i) { mbar_init(bar_S + 8 * i, 1); mbar_init(bar_P + 8 * i, 4); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_O + 8 * i, 1); mbar_init(bar_Q + 8 * i, 4); }
     mbar_fence_init();
+#if T2_WATCH
+    *reinterpret_cast<volatile uint32_t*>(bp + T2_OFF_BARS + 168) = 0u;
+    *reinterpret_cast<volatile uint32_t*>(bp + T2_OFF_BARS + 172) = 0u;
+    *reinterpret_cast<volatile uint32_t*>(bp + T2_OFF_BARS + 176) = 0u;
+#endif
   }
   // constant selector B tile: element [key, 16 i + c] = 1 iff c / 4 == i and c % 4 < 3
   for (int idx = tid; idx < 64 * 8; idx += TC_THREADS) {
@@ -863,7 +878,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc2_kernel(const A
         T2_TICK(5);
 #else
         softmax_chunk(ra, db, ls);
+#if T2_WATCH
+        // S_ready of the next unit through the watcher's counter: a shared-memory load instead of a barrier test (the test stalls
+        // the warp ~180 cycles even when the phase is complete — 7 % of all samples in profiles/attn_tc_lines_r02h.txt)
+        if (u + 1 < total) s_ok = lds_acquire(wflag + 4 * g) >= (uint32_t)(u + 2);
+#else
         if (u + 1 < total) s_ok = mbar_test_wait(nbarS, nparS);
+#endif
         if (i == 3 && j + 1 < nblk) f_ok = mbar_test_wait(bar_full + 8 * ((j + 1) % T2_STAGES), (uint32_t)(((j + 1) / T2_STAGES) & 1));
         tmem_st32_nowait(slot, ra);
         T2_TICK(3);
@@ -886,6 +907,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc2_kernel(const A
 #endif
       }
     }
+#if T2_WATCH
+    __syncwarp();
+    if (lane == 0) atomicAdd(reinterpret_cast<unsigned int*>(bp + T2_OFF_BARS + 176), 1u);   // lets the watcher leave
+#endif
 #if T2_PIPE
     if (nblk > 0) {                                               // P of the last unit
       tmem_wait_st();
@@ -1003,6 +1028,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spatial_attn_tc2_kernel(const A
     }
     __syncwarp();
     }
+#if T2_WATCH
+    else {
+    // =========================================================================== watcher (the fourth role warp)
+    // Polls the S_ready barriers of both head groups in unit order and publishes how many units are ready, so that the softmax
+    // warps learn it from a shared-memory load. Observing a barrier with acquire semantics and releasing the counter orders the
+    // MMA's TMEM writes before any softmax thread that acquires the counter. If the watcher ever lags (or mis-reads a barrier
+    // that has run two phases ahead) the counter merely stays behind and the softmax warps fall back to the barrier itself.
+    if (nblk > 0 && elect_one()) {
+      const int total = 4 * nblk;
+      int c0 = 0, c1 = 0;
+      while (c0 < total || c1 < total) {
+        if (c0 < total && mbar_test_wait(bar_S + 8 * (c0 % 3), (uint32_t)((c0 / 3) & 1))) { ++c0; sts_release(wflag, (uint32_t)c0); }
+        if (c1 < total && mbar_test_wait(bar_S + 8 * (3 + c1 % 3), (uint32_t)((c1 / 3) & 1))) { ++c1; sts_release(wflag + 4, (uint32_t)c1); }
+        if (lds_acquire(wflag + 8) >= 8u) break;                   // every softmax warp has left its loop
+      }
+    }
+    __syncwarp();
+    }
+#endif
   }
   fence_before();
   __syncthreads();

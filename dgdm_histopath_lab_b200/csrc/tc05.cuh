@@ -88,6 +88,16 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, u
   }
 }
 
+// release / acquire accesses to a shared-memory word (flags between warps of a CTA; no mbarrier instruction involved)
+__device__ __forceinline__ uint32_t lds_acquire(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_release(uint32_t saddr, uint32_t v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
